@@ -1,0 +1,63 @@
+"""ctypes binding of the C-ABI library (include/hplflownet_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, an exception is
+raised.  The library is built in-tree by ``python -m hplflownet_b200.build``
+(``__graft_entry__.build()`` does it).
+"""
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libhplflownet_b200.so")
+
+i64, i32, vp, cint = ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int
+
+# name -> argtypes; every function returns int (0 = ok).  Mirrors include/hplflownet_b200.h.
+SIGNATURES = {
+    "hpl_version": [],
+    "hpl_sm_arch": [],
+    "hpl_scatter_rows": [vp, vp, vp, cint, i64, i64, vp, i64, vp, vp],
+    "hpl_normalize_rows": [vp, i64, i64, i64, vp, vp, vp],
+    "hpl_gather_rows": [vp, i64, vp, vp, cint, vp, vp, i64, i64, vp, vp],
+    "hpl_blur_gemm": [vp, i64, i64, vp, cint, i64, i64, i64, i64, vp, vp, cint, vp, i64, cint, cint, vp],
+    "hpl_blur_wgrad": [vp, i64, i64, vp, cint, i64, i64, i64, i64, vp, i64, vp, vp, vp],
+    "hpl_act_backward": [vp, i64, vp, i64, i64, i64, cint, vp],
+    "hpl_transpose_table": [vp, cint, i64, i64, vp, i64, vp, vp],
+    "hpl_cm_to_rows": [vp, i64, i64, i64, vp, i64, vp],
+    "hpl_rows_to_cm": [vp, i64, i64, i64, vp, i64, vp],
+    "hpl_channel_sums": [vp, i64, i64, vp, vp],
+    "hpl_fill_zero": [vp, i64, vp],
+    "hpl_fill_i32": [vp, i64, i32, vp],
+}
+
+
+class HplError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "hplflownet_b200: %s is missing -- build it with `python -m hplflownet_b200.build` "
+                "(there is no CPU or PyTorch fallback for this path)" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError if the .so is stale
+            fn.argtypes = args
+            fn.restype = cint
+        _lib = lib
+    return _lib
+
+
+def call(name, *args):
+    """Invoke an ABI entry point; raise HplError on a non-zero return code."""
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        detail = "argument error" if rc < 0 else "CUDA error %d" % rc
+        raise HplError("%s failed: %s (rc=%d)" % (name, detail, rc))

@@ -1,0 +1,213 @@
+"""B200-native ``BilateralConvFlex`` -- drop-in for models/bilateralNN.py:46-238.
+
+Same constructor, forward signature, return shapes and ``state_dict`` layout as the reference
+module, so ``models/HPLFlowNet.py`` runs on top of it unchanged.  The forward and the backward
+are hand-written sm_100a kernels behind the C ABI (include/hplflownet_b200.h):
+
+  splat   (:150-186)  scatter-add of barycentric-weighted features into vertex-major lattice
+                      rows + density normalisation -- replaces two sparse-COO densifications;
+  blur    (:198-221)  gather-GEMM over the neighbour table with fused bias + (Leaky)ReLU --
+                      the F-times gathered copy (:215-217) never exists, so no chunking;
+  slice   (:223-238)  barycentric gather of 4 lattice rows per point (+ bias).
+
+``SparseSum`` / ``sparse_sum`` (:9-43) are kept as public names on top of the same scatter
+kernel.  There is no CPU path: tensors must live on a CUDA device.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .module_utils import Conv2dReLU
+
+__all__ = ["BilateralConvFlex", "SparseSum", "sparse_sum"]
+
+
+def _act_code(has_act, use_leaky):
+    if not has_act:
+        return ops.ACT_NONE
+    return ops.ACT_LEAKY if use_leaky else ops.ACT_RELU
+
+
+class SparseSum(torch.autograd.Function):
+    """Dense ``out[idx[m], :] += values[m, :]`` (models/bilateralNN.py:9-40).
+
+    Kept for API parity; runs the splat scatter kernel with unit weights on remainder 0.
+    ``indices`` (1, M) int64, ``values`` (M, C) -> (size[0], C).
+    """
+
+    @staticmethod
+    def forward(ctx, indices, values, size, cuda=True):
+        ctx.save_for_backward(indices)
+        m, c = values.shape
+        x = values.t().contiguous()                                        # (C, M)
+        off = torch.full((4, m), -1, dtype=torch.int64, device=values.device)
+        off[0] = indices.reshape(-1)                                       # remainders 1..3 unused
+        ones = torch.ones((4, m), dtype=torch.float32, device=values.device)
+        rows, _ = ops.scatter_rows(x, ones, off, int(size[0]), False)
+        return rows[:, :c].contiguous()
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        indices, = ctx.saved_tensors
+        grad_values = grad_output[indices.squeeze(0), :] if ctx.needs_input_grad[1] else None
+        return None, grad_values, None, None
+
+
+sparse_sum = SparseSum.apply
+
+
+class _BCLFunction(torch.autograd.Function):
+    """splat -> conv stack -> slice with a hand-written backward (autograd in the reference)."""
+
+    @staticmethod
+    def forward(ctx, cfg, features, in_bary, in_off, nbr, out_bary, out_off, slice_bias, *params):
+        do_splat, do_slice, use_norm, acts = cfg
+        dev = features.device
+        feat = features[0].contiguous()                      # (C, N) -- B = 1 (README.md:57)
+        c_in = feat.size(0)
+        nbr2 = nbr[0].contiguous()                           # (F, H)
+        filter_size, h = nbr2.shape
+        inv = None
+        if do_splat:
+            bary_i, off_i = in_bary[0].contiguous(), in_off[0].contiguous()
+            lat, wsum = ops.scatter_rows(feat, bary_i, off_i, h, use_norm)
+            if use_norm:
+                inv = ops.normalize_rows_(lat, c_in, wsum)
+        else:
+            bary_i = off_i = None
+            lat = ops.cm_to_rows(feat)
+
+        n_layers = len(params) // 2
+        xs = [lat]                                           # xs[l] = input of layer l (vertex-major)
+        chans = [c_in]
+        wts = []
+        x = lat
+        y_cm = None
+        for l in range(n_layers):
+            w, b = params[2 * l], params[2 * l + 1]
+            wt = w.detach()[:, :, :, 0].permute(2, 1, 0).contiguous()    # (F or 1, C, Co)
+            wts.append(wt)
+            co = wt.size(2)
+            last = l == n_layers - 1
+            direct_cm = last and not do_slice and acts[l] == ops.ACT_NONE
+            x = ops.blur_gemm(x, chans[-1], nbr2 if l == 0 else None, h, wt, b.detach(), acts[l],
+                              out_channel_major=direct_cm)
+            if direct_cm:
+                y_cm = x
+            else:
+                xs.append(x)
+            chans.append(co)
+
+        if do_slice:
+            bary_o, off_o = out_bary[0].contiguous(), out_off[0].contiguous()
+            out = ops.gather_rows(x, chans[-1], bary_o, off_o, None,
+                                  slice_bias.detach() if slice_bias is not None else None)
+        else:
+            bary_o = off_o = None
+            out = y_cm if y_cm is not None else ops.rows_to_cm(x, chans[-1])
+
+        ctx.cfg, ctx.chans, ctx.h, ctx.filter_size = cfg, chans, h, filter_size
+        ctx.xs, ctx.wts, ctx.inv = xs, wts, inv
+        ctx.idx = (bary_i, off_i, nbr2, bary_o, off_o)
+        ctx.has_slice_bias = slice_bias is not None
+        return out.unsqueeze(0)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        do_splat, do_slice, use_norm, acts = ctx.cfg
+        bary_i, off_i, nbr2, bary_o, off_o = ctx.idx
+        chans, h, xs, wts = ctx.chans, ctx.h, ctx.xs, ctx.wts
+        n_layers = len(wts)
+        g = grad_out[0].contiguous()
+        d_slice_bias = None
+        if do_slice:
+            dx, _ = ops.scatter_rows(g, bary_o, off_o, h, False)
+            if ctx.has_slice_bias and ctx.needs_input_grad[7]:
+                d_slice_bias = ops.channel_sums(g)
+        else:
+            dx = ops.cm_to_rows(g)
+
+        grads = [None] * (2 * n_layers)
+        need_feat = ctx.needs_input_grad[1]
+        for l in range(n_layers - 1, -1, -1):
+            if acts[l] != ops.ACT_NONE:
+                ops.act_backward_(dx, xs[l + 1], chans[l + 1], acts[l])
+            tbl = nbr2 if l == 0 else None
+            fs = ctx.filter_size if l == 0 else 1
+            if ctx.needs_input_grad[8 + 2 * l] or ctx.needs_input_grad[9 + 2 * l]:
+                dw, db = ops.blur_wgrad(xs[l], chans[l], tbl, h, dx, chans[l + 1], fs)
+                grads[2 * l] = dw.permute(2, 1, 0).unsqueeze(-1).contiguous()      # (Co, C, F, 1)
+                grads[2 * l + 1] = db
+            if l > 0 or need_feat:
+                wd = wts[l].transpose(1, 2).contiguous()                           # (F, Co, C)
+                tbl_t = ops.transpose_table(nbr2, h) if l == 0 else None
+                dx = ops.blur_gemm(dx, chans[l + 1], tbl_t, h, wd, None, ops.ACT_NONE)
+
+        d_feat = None
+        if need_feat:
+            if do_splat:
+                d_feat = ops.gather_rows(dx, chans[0], bary_i, off_i, ctx.inv, None).unsqueeze(0)
+            else:
+                d_feat = ops.rows_to_cm(dx, chans[0]).unsqueeze(0)
+        return (None, d_feat, None, None, None, None, None, d_slice_bias, *grads)
+
+
+class BilateralConvFlex(nn.Module):
+    """Same interface as the reference module (models/bilateralNN.py:46-125)."""
+
+    def __init__(self, d, neighborhood_size, num_input, num_output, DEVICE, use_bias, use_leaky, use_norm,
+                 do_splat, do_slice, last_relu, chunk_size=1024 * 1024 * 25):
+        super().__init__()
+        self.d, self.d1 = d, d + 1
+        self.neighborhood_size = neighborhood_size
+        self.filter_size = self.get_filter_size()
+        self.num_input, self.num_output = num_input, list(num_output)
+        self.DEVICE = DEVICE
+        self.use_bias, self.use_leaky, self.use_norm = use_bias, use_leaky, use_norm
+        self.do_splat, self.do_slice, self.last_relu = do_splat, do_slice, last_relu
+        self.MAX_SIZE = chunk_size      # accepted for compatibility; the fused path never chunks
+
+        c_final = self.num_output[-1]
+        # index buffers the reference registers (:90-92); unused here, kept for strict loading
+        self.register_buffer("feat_indices", torch.arange(num_input, dtype=torch.long))
+        if do_slice:
+            self.register_buffer("out_indices", torch.arange(c_final, dtype=torch.long))
+
+        layers, c_prev = [], num_input
+        widths = self.num_output
+        for i, c_out in enumerate(widths):
+            ks = (self.filter_size, 1) if i == 0 else (1, 1)
+            is_last = i == len(widths) - 1
+            if is_last and not last_relu:
+                layers.append(nn.Conv2d(c_prev, c_out, kernel_size=ks))
+            else:
+                layers.append(Conv2dReLU(c_prev, c_out, ks, use_leaky=use_leaky))
+            c_prev = c_out
+        self.blur_conv = nn.Sequential(*layers)
+
+        if do_slice and use_bias:
+            self.register_parameter("bias", nn.Parameter(torch.zeros(c_final, dtype=torch.float32)))
+
+    def get_filter_size(self):
+        return (self.neighborhood_size + 1) ** self.d1 - self.neighborhood_size ** self.d1
+
+    def _layer_params(self):
+        params, acts = [], []
+        for layer in self.blur_conv:
+            conv = layer.conv if isinstance(layer, Conv2dReLU) else layer
+            params += [conv.weight, conv.bias]
+            acts.append(_act_code(isinstance(layer, Conv2dReLU), self.use_leaky))
+        return params, tuple(acts)
+
+    def forward(self, features, in_barycentric, in_lattice_offset, blur_neighbors, out_barycentric,
+                out_lattice_offset):
+        """features (1, C_in, N_in | H) -> (1, C_out, N_out | H); see models/bilateralNN.py:122-135."""
+        if features.size(0) != 1:
+            raise ValueError("batch size must be 1 (reference README.md:57); concatenate clouds instead")
+        if not features.is_cuda:
+            raise RuntimeError("BilateralConvFlex (B200) has no CPU path: inputs must be CUDA tensors")
+        params, acts = self._layer_params()
+        cfg = (self.do_splat, self.do_slice, self.use_norm, acts)
+        bias = self.bias if (self.do_slice and self.use_bias) else None
+        return _BCLFunction.apply(cfg, features, in_barycentric, in_lattice_offset, blur_neighbors,
+                                  out_barycentric, out_lattice_offset, bias, *params)

@@ -1,0 +1,150 @@
+"""Tensor-level wrappers over the C ABI (include/hplflownet_b200.h).
+
+PyTorch is used for device memory and streams only: every function checks its arguments,
+allocates outputs with torch, and enqueues the hand-written CUDA kernels on the current stream.
+Lattice values are vertex-major ``(rows, ld)`` fp32 tensors with ``ld % 4 == 0``.
+"""
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(x, name):
+    if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
+        raise ValueError("%s must be a contiguous CUDA float32 tensor" % name)
+    return x
+
+
+def _idx(x, name):
+    if not (x.is_cuda and x.dtype in (torch.int64, torch.int32) and x.is_contiguous()):
+        raise ValueError("%s must be a contiguous CUDA int64/int32 tensor" % name)
+    return x, int(x.dtype == torch.int64)
+
+
+def round4(c):
+    return (int(c) + 3) // 4 * 4
+
+
+def alloc_rows(n_rows, channels, device, zero=False):
+    """(n_rows, round4(channels)) fp32; pad columns are always zero."""
+    ld = round4(channels)
+    if zero or ld != channels:
+        return torch.zeros((n_rows, ld), dtype=torch.float32, device=device)
+    return torch.empty((n_rows, ld), dtype=torch.float32, device=device)
+
+
+def scatter_rows(x, bary, off, n_rows, want_wsum):
+    """x (C, N), bary (4, N), off (4, N) -> rows (n_rows, ld) [, wsum (n_rows)]."""
+    _f32(x, "x"); _f32(bary, "bary")
+    off, i64 = _idx(off, "off")
+    c, n = x.shape
+    rows = alloc_rows(n_rows, c, x.device, zero=True)
+    wsum = torch.zeros(n_rows, dtype=torch.float32, device=x.device) if want_wsum else None
+    _lib.call("hpl_scatter_rows", x.data_ptr(), bary.data_ptr(), off.data_ptr(), i64, n, c,
+              rows.data_ptr(), rows.stride(0), wsum.data_ptr() if want_wsum else None, _stream())
+    return rows, wsum
+
+
+def normalize_rows_(rows, channels, wsum):
+    """In place: rows *= 1/(wsum+1e-5); wsum becomes the reciprocal (returned)."""
+    _lib.call("hpl_normalize_rows", rows.data_ptr(), rows.stride(0), rows.size(0), channels,
+              wsum.data_ptr(), wsum.data_ptr(), _stream())
+    return wsum
+
+
+def gather_rows(rows, channels, bary, off, scale=None, bias=None):
+    """rows (H, ld) -> y (C, N)."""
+    _f32(rows, "rows"); _f32(bary, "bary")
+    off, i64 = _idx(off, "off")
+    n = bary.size(-1)
+    y = torch.empty((channels, n), dtype=torch.float32, device=rows.device)
+    _lib.call("hpl_gather_rows", rows.data_ptr(), rows.stride(0), bary.data_ptr(), off.data_ptr(), i64,
+              scale.data_ptr() if scale is not None else None,
+              bias.data_ptr() if bias is not None else None, n, channels, y.data_ptr(), _stream())
+    return y
+
+
+def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_major=False, precision=0):
+    """out[v] = act(bias + sum_f x[nbr[f, v]] @ w[f]);  w (F, C, Co)."""
+    _f32(x, "x"); _f32(w, "w")
+    f, c, co = w.shape
+    assert c == c_in
+    if nbr is not None:
+        nbr, i64 = _idx(nbr, "nbr")
+        assert nbr.shape[-2] == f and nbr.shape[-1] == n_out_rows
+        nbr_ptr = nbr.data_ptr()
+    else:
+        assert f == 1
+        nbr_ptr, i64 = None, 0
+    if out is None:
+        out = (torch.empty((co, n_out_rows), dtype=torch.float32, device=x.device) if out_channel_major
+               else alloc_rows(n_out_rows, co, x.device))
+    _lib.call("hpl_blur_gemm", x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, f, n_out_rows, c, co,
+              w.data_ptr(), bias.data_ptr() if bias is not None else None, act, out.data_ptr(),
+              out.stride(0), int(out_channel_major), precision, _stream())
+    return out
+
+
+def blur_wgrad(x, c_in, nbr, n_out_rows, dz, c_out, filter_size, want_db=True):
+    """Returns dw (F, C, Co), db (Co)."""
+    _f32(x, "x"); _f32(dz, "dz")
+    if nbr is not None:
+        nbr, i64 = _idx(nbr, "nbr")
+        nbr_ptr = nbr.data_ptr()
+    else:
+        nbr_ptr, i64 = None, 0
+    dw = torch.zeros((filter_size, c_in, c_out), dtype=torch.float32, device=x.device)
+    db = torch.zeros(c_out, dtype=torch.float32, device=x.device) if want_db else None
+    _lib.call("hpl_blur_wgrad", x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, filter_size, n_out_rows,
+              c_in, c_out, dz.data_ptr(), dz.stride(0), dw.data_ptr(), db.data_ptr() if want_db else None,
+              _stream())
+    return dw, db
+
+
+def act_backward_(dz, y, channels, act):
+    if act != ACT_NONE:
+        _lib.call("hpl_act_backward", dz.data_ptr(), dz.stride(0), y.data_ptr(), y.stride(0), dz.size(0),
+                  channels, act, _stream())
+    return dz
+
+
+def transpose_table(tbl, n_src_rows):
+    """tbl (F, n) -> int32 (F, n_src_rows) with t[f, tbl[f, v]] = v, -1 elsewhere."""
+    tbl, i64 = _idx(tbl, "tbl")
+    f, n = tbl.shape[-2], tbl.shape[-1]
+    out = torch.empty((f, n_src_rows), dtype=torch.int32, device=tbl.device)
+    _lib.call("hpl_fill_i32", out.data_ptr(), out.numel(), -1, _stream())
+    _lib.call("hpl_transpose_table", tbl.data_ptr(), i64, f, n, out.data_ptr(), n_src_rows, None, _stream())
+    return out
+
+
+def cm_to_rows(cm):
+    """(C, n) channel-major -> (n, ld) vertex-major."""
+    _f32(cm, "cm")
+    c, n = cm.shape
+    rows = torch.empty((n, round4(c)), dtype=torch.float32, device=cm.device)
+    _lib.call("hpl_cm_to_rows", cm.data_ptr(), cm.stride(0), n, c, rows.data_ptr(), rows.stride(0), _stream())
+    return rows
+
+
+def rows_to_cm(rows, channels):
+    _f32(rows, "rows")
+    n = rows.size(0)
+    cm = torch.empty((channels, n), dtype=torch.float32, device=rows.device)
+    _lib.call("hpl_rows_to_cm", rows.data_ptr(), rows.stride(0), n, channels, cm.data_ptr(), cm.stride(0),
+              _stream())
+    return cm
+
+
+def channel_sums(x):
+    _f32(x, "x")
+    c, n = x.shape
+    s = torch.zeros(c, dtype=torch.float32, device=x.device)
+    _lib.call("hpl_channel_sums", x.data_ptr(), c, n, s.data_ptr(), _stream())
+    return s

@@ -1,0 +1,125 @@
+/*
+ * hplflownet_b200.h -- C ABI of the B200-native bilateral-convolution-layer path.
+ *
+ * Drop-in boundary for the hot path of laoreja/HPLFlowNet:
+ *   index half : transforms/transforms.py:264-485 (GenerateDataUnsymmetric) and its only
+ *                native dependency, the khash int64 map (models/khash_int2int.h:8-33,
+ *                bound through cffi in models/build_khash_cffi.py:15-22 and called from
+ *                Numba in transforms/transforms.py:20-24,170-261);
+ *   value half : models/bilateralNN.py:9-238 (SparseSum, BilateralConvFlex) and
+ *                models/bnn_flow.py:96-210 (BilateralCorrelationFlex), which the
+ *                reference runs as stock PyTorch ops.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - every function returns 0 on success, a cudaError_t value (>0) when the CUDA runtime
+ *     reports an error, or a negative HPL_E* code for argument errors; nothing is
+ *     synchronised -- work is enqueued on `stream`;
+ *   - B = 1 as in the reference (README.md:57); several clouds are processed in one call by
+ *     concatenating their points/vertices (tables carry global row numbers);
+ *   - lattice values live VERTEX-MAJOR in HBM: a (rows, ld) fp32 matrix, one contiguous row
+ *     of `ld >= C` floats per lattice vertex, ld % 4 == 0, 16-byte aligned.  There is no
+ *     physical "null vertex" row: a table entry of -1 (bilateralNN.py:158-159) reads as zeros;
+ *   - point features cross the boundary CHANNEL-MAJOR (C, N) exactly as the reference modules
+ *     take them (bilateralNN.py:128-134);
+ *   - index tables are int64 (idx64 != 0; what the reference hands over) or int32.
+ */
+#ifndef HPLFLOWNET_B200_H
+#define HPLFLOWNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HPL_EINVAL (-1)   /* bad argument (null pointer, misaligned ld, unsupported size) */
+#define HPL_ENOSPC (-2)   /* caller-provided capacity too small */
+
+#define HPL_ACT_NONE 0
+#define HPL_ACT_RELU 1
+#define HPL_ACT_LEAKY 2   /* LeakyReLU(0.1), models/module_utils.py:6 */
+
+/* Library / build identification. */
+int hpl_version(void);
+/* Compiled SM architecture (100 for sm_100a). */
+int hpl_sm_arch(void);
+
+/* ---------------------------------------------------------------- value half */
+
+/* SPLAT (scatter half of SparseSum + splat, bilateralNN.py:9-30,150-166; also the backward of
+ * SLICE, :226-232):   rows[off[r,n], c] += bary[r,n] * x[c,n]      r < 4
+ * and, when wsum != NULL,   wsum[off[r,n]] += bary[r,n]              (:168-182).
+ * x (C, N) channel-major; bary (4, N); off (4, N) in [0, H); rows (H, ld) and wsum (H) must be
+ * zeroed by the caller (hpl_fill_zero).  Accumulation order is not deterministic (fp32 RED). */
+int hpl_scatter_rows(const float* x, const float* bary, const void* off, int idx64,
+                     int64_t n_points, int64_t channels, float* rows, int64_t ld, float* wsum,
+                     void* stream);
+
+/* Density normalisation (bilateralNN.py:185-186):  inv[v] = 1/(wsum[v] + 1e-5),
+ * rows[v, :] *= inv[v].  inv may alias wsum. */
+int hpl_normalize_rows(float* rows, int64_t ld, int64_t n_rows, int64_t channels,
+                       const float* wsum, float* inv, void* stream);
+
+/* SLICE (bilateralNN.py:226-236; also the backward of SPLAT, :33-40):
+ *   y[c,n] = sum_r bary[r,n] * scale[off[r,n]] * rows[off[r,n], c]  (+ bias[c])
+ * scale (H) and bias (C) may be NULL. y (C, N) channel-major. */
+int hpl_gather_rows(const float* rows, int64_t ld, const float* bary, const void* off, int idx64,
+                    const float* scale, const float* bias, int64_t n_points, int64_t channels,
+                    float* y, void* stream);
+
+/* BLUR / learned convolution over lattice neighbours (bilateralNN.py:198-221 with the conv
+ * built at :94-113), as a gather-GEMM with fused bias + activation:
+ *   out[v, o] = act( bias[o] + sum_{f<F} sum_{c<C} in[nbr[f,v], c] * w[f, c, o] )
+ * in (n_in_rows, ld_in) vertex-major; nbr (F, n_out_rows) in [-1, n_in_rows), -1 reads zeros;
+ * nbr == NULL means F == 1 and row v reads row v (the 1x1 layers, :99-100).
+ * w (F, C, Co) fp32 -- the reference's (Co, C, F, 1) weight permuted (2,1,0).
+ * out (n_out_rows, ld_out) vertex-major, or, when out_channel_major != 0, (Co, ld_out)
+ * channel-major with ld_out >= n_out_rows (the module's (B, Co, H) result, :221).
+ * The same entry point is the data-gradient of the layer when called with the transposed
+ * table (hpl_transpose_table) and w permuted to (F, Co, C).
+ * precision: 0 = fp32 FMA on CUDA cores (parity anchor). */
+int hpl_blur_gemm(const float* in, int64_t ld_in, int64_t n_in_rows, const void* nbr, int idx64,
+                  int64_t filter_size, int64_t n_out_rows, int64_t c_in, int64_t c_out,
+                  const float* w, const float* bias, int act, float* out, int64_t ld_out,
+                  int out_channel_major, int precision, void* stream);
+
+/* Weight gradient of the layer above:
+ *   dw[f, c, o] += sum_v in[nbr[f,v], c] * dz[v, o]        db[o] += sum_v dz[v, o]
+ * dw (F, C, Co) and db (Co, may be NULL) must be zeroed by the caller; partial sums over
+ * vertex ranges are combined with fp32 RED. */
+int hpl_blur_wgrad(const float* in, int64_t ld_in, int64_t n_in_rows, const void* nbr, int idx64,
+                   int64_t filter_size, int64_t n_out_rows, int64_t c_in, int64_t c_out,
+                   const float* dz, int64_t ld_dz, float* dw, float* db, void* stream);
+
+/* Activation backward, in place:  dz[v, c] *= (y[v, c] > 0 ? 1 : slope(act)).
+ * LeakyReLU/ReLU keep the sign, so the saved output is enough (module_utils.py:34). */
+int hpl_act_backward(float* dz, int64_t ld_dz, const float* y, int64_t ld_y, int64_t n_rows,
+                     int64_t channels, int act, void* stream);
+
+/* tbl_t[f, tbl[f, v]] = v for every tbl[f, v] >= 0; tbl_t (F, n_src_rows) int32 must be
+ * pre-filled with -1 (hpl_fill_i32).  tbl (F, n_rows).  Used to turn the scatter in the
+ * data-gradient of BLUR into a gather.  *collisions (device int32, may be NULL) counts
+ * entries that found their slot taken (a non-injective table; never produced by the
+ * lattice builder). */
+int hpl_transpose_table(const void* tbl, int idx64, int64_t filter_size, int64_t n_rows,
+                        int32_t* tbl_t, int64_t n_src_rows, int32_t* collisions, void* stream);
+
+/* Layout changes at the module boundary (bilateralNN.py:190-196, :221-224):
+ *   cm (C, ld_cm) channel-major  <->  rows (n, ld) vertex-major. */
+int hpl_cm_to_rows(const float* cm, int64_t ld_cm, int64_t n, int64_t channels, float* rows,
+                   int64_t ld, void* stream);
+int hpl_rows_to_cm(const float* rows, int64_t ld, int64_t n, int64_t channels, float* cm,
+                   int64_t ld_cm, void* stream);
+
+/* sums[c] += sum_n x[c, n]   (bias gradient of SLICE, bilateralNN.py:235-236). x (C, N). */
+int hpl_channel_sums(const float* x, int64_t channels, int64_t n, float* sums, void* stream);
+
+int hpl_fill_zero(void* ptr, int64_t bytes, void* stream);
+int hpl_fill_i32(int32_t* ptr, int64_t count, int32_t value, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HPLFLOWNET_B200_H */

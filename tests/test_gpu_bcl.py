@@ -1,0 +1,140 @@
+"""GPU parity of BilateralConvFlex (through the C ABI) against (a) fixtures dumped from the
+unmodified reference and (b) the oracle on seeded inputs up to BASELINE size.
+
+Tolerance: 1e-5 relative per tensor (north_star); scatter-add order is not deterministic."""
+import numpy as np
+import pytest
+import torch
+
+import hplflownet_b200 as hpl
+from oracle import bcl as OB
+from oracle import lattice as OL
+from tests._util import assert_close, golden, golden_files, grads_from, state_from, t
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _module_from_golden(g):
+    c_in, do_splat, do_slice, use_norm, use_leaky, use_bias, last_relu = [int(x) for x in g["cfg"]]
+    mod = hpl.BilateralConvFlex(3, 1, c_in, [int(c) for c in g["c_out"]], "cuda", use_bias=bool(use_bias),
+                                use_leaky=bool(use_leaky), use_norm=bool(use_norm), do_splat=bool(do_splat),
+                                do_slice=bool(do_slice), last_relu=bool(last_relu), chunk_size=-1)
+    mod.load_state_dict(state_from(g), strict=True)
+    return mod.to(DEV), bool(do_splat), bool(do_slice)
+
+
+@pytest.mark.parametrize("name", golden_files("bcl_"))
+def test_bcl_matches_reference_fixture(name):
+    g = golden(name)
+    mod, do_splat, do_slice = _module_from_golden(g)
+    feat = t(g["features"], DEV).requires_grad_(True)
+    bary, off, nbr = t(g["barycentric"], DEV), t(g["lattice_offset"], DEV), t(g["blur_neighbors"], DEV)
+    y = mod(feat, bary if do_splat else None, off if do_splat else None, nbr,
+            bary if do_slice else None, off if do_slice else None)
+    assert_close(y, g["output"], "output")
+    y.backward(t(g["grad_output"], DEV))
+    assert_close(feat.grad, g["grad_features"], "grad_features")
+    got = dict(mod.named_parameters())
+    for k, ref in grads_from(g).items():
+        assert_close(got[k].grad, ref, "grad " + k)
+
+
+def _lattice(n, seed, scale):
+    from hplflownet_b200.synthetic import frustum_pair
+    pc1, pc2 = frustum_pair(n, seed)
+    d = OL.generate(pc1, pc2, [[scale, 1, -1, -1]])[0]
+    return {k: (torch.from_numpy(v)[None] if not isinstance(v, int) else v) for k, v in d.items()}
+
+
+@pytest.mark.parametrize("n,c_in,c_out,scale,idx_dtype", [
+    (2048, 16, [16], 1.0, torch.int64),          # BASELINE configs[0]
+    (8192, 64, [64], 1.0, torch.int64),          # BASELINE configs[1]
+    (8192, 64, [64], 3.0, torch.int32),          # finest level of the net, native int32 tables
+    (1000, 68, [64, 64], 2.0, torch.int64),      # bcn1-style down layer (HPLFlowNet.py:26-35)
+    (777, 7, [5, 3], 1.0, torch.int64),          # channel counts that are not multiples of 4
+])
+def test_bcl_matches_oracle(n, c_in, c_out, scale, idx_dtype):
+    d = _lattice(n, 3, scale)
+    torch.manual_seed(0)
+    mod = hpl.BilateralConvFlex(3, 1, c_in, c_out, "cuda", use_bias=True, use_leaky=True, use_norm=True,
+                                do_splat=True, do_slice=True, last_relu=False, chunk_size=-1)
+    with torch.no_grad():
+        mod.bias.normal_(0, 0.3)
+    state = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in mod.state_dict().items()}
+    mod = mod.to(DEV)
+    feat = torch.randn(1, c_in, n)
+    gy = torch.randn(1, c_out[-1], n)
+    bary, off, nbr = d["pc1_barycentric"], d["pc1_lattice_offset"], d["pc1_blur_neighbors"]
+
+    f_ref = feat.clone().requires_grad_(True)
+    y_ref = OB.bcl_forward(state, f_ref, bary, off, nbr, bary, off, do_splat=True, do_slice=True,
+                           use_norm=True, use_leaky=True, use_bias=True)
+    y_ref.backward(gy)
+
+    f = feat.to(DEV).requires_grad_(True)
+    bg, og, ng = bary.to(DEV), off.to(DEV).to(idx_dtype), nbr.to(DEV).to(idx_dtype)
+    y = mod(f, bg, og, ng, bg, og)
+    y.backward(gy.to(DEV))
+    assert_close(y, y_ref.detach(), "output")
+    assert_close(f.grad, f_ref.grad, "grad_features")
+    for k, p in mod.named_parameters():
+        assert_close(p.grad, state[k].grad, "grad " + k)
+
+
+def test_no_slice_no_splat_layouts():
+    # up/down-path shapes: (1, C, H) in and out (HPLFlowNet.py:242-246, :372-377)
+    d = _lattice(1500, 9, 1.0)
+    h = d["pc1_hash_cnt"]
+    nbr = d["pc1_blur_neighbors"]
+    torch.manual_seed(1)
+    for last_relu in (False, True):
+        mod = hpl.BilateralConvFlex(3, 1, 12, [20, 8], "cuda", use_bias=True, use_leaky=True, use_norm=True,
+                                    do_splat=False, do_slice=False, last_relu=last_relu, chunk_size=-1)
+        state = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in mod.state_dict().items()}
+        mod = mod.to(DEV)
+        feat = torch.randn(1, 12, h)
+        gy = torch.randn(1, 8, h)
+        f_ref = feat.clone().requires_grad_(True)
+        y_ref = OB.bcl_forward(state, f_ref, None, None, nbr, None, None, do_splat=False, do_slice=False,
+                               use_norm=True, use_leaky=True, use_bias=True)
+        y_ref.backward(gy)
+        f = feat.to(DEV).requires_grad_(True)
+        y = mod(f, None, None, nbr.to(DEV), None, None)
+        y.backward(gy.to(DEV))
+        assert y.shape == (1, 8, h)
+        assert_close(y, y_ref.detach(), "output")
+        assert_close(f.grad, f_ref.grad, "grad_features")
+        for k, p in mod.named_parameters():
+            assert_close(p.grad, state[k].grad, "grad " + k)
+
+
+def test_sparse_sum_matches_index_add():
+    torch.manual_seed(0)
+    m, c, rows = 5000, 10, 321
+    idx = torch.randint(0, rows, (1, m), device=DEV)
+    vals = torch.randn(m, c, device=DEV, requires_grad=True)
+    out = hpl.sparse_sum(idx, vals, torch.Size([rows, c]), True)
+    ref = torch.zeros(rows, c, device=DEV).index_add_(0, idx[0], vals.detach())
+    assert_close(out, ref, "sparse_sum")
+    out.sum().backward()
+    assert torch.equal(vals.grad, torch.ones_like(vals))
+
+
+def test_linearity_and_null_vertex():
+    # size-independent properties: splat/blur/slice with identity activation is linear in the
+    # features, and a table full of -1 (all neighbours missing) yields exactly the conv bias.
+    d = _lattice(4096, 5, 1.0)
+    bary, off, nbr = [d[k].to(DEV) for k in ("pc1_barycentric", "pc1_lattice_offset", "pc1_blur_neighbors")]
+    mod = hpl.BilateralConvFlex(3, 1, 8, [8], "cuda", use_bias=False, use_leaky=True, use_norm=True,
+                                do_splat=True, do_slice=True, last_relu=False, chunk_size=-1).to(DEV)
+    with torch.no_grad():
+        mod.blur_conv[0].bias.zero_()
+        a, b = torch.randn(1, 8, 4096, device=DEV), torch.randn(1, 8, 4096, device=DEV)
+        ya, yb, yab = mod(a, bary, off, nbr, bary, off), mod(b, bary, off, nbr, bary, off), \
+            mod(2 * a - 3 * b, bary, off, nbr, bary, off)
+        assert_close(yab, 2 * ya - 3 * yb, "linearity", tol=2e-5)
+        mod.blur_conv[0].bias.normal_()
+        y = mod(a, bary, off, torch.full_like(nbr, -1), bary, off)
+        want = mod.blur_conv[0].bias[None, :, None] * bary.sum(1, keepdim=True)
+        assert_close(y, want.expand_as(y), "null vertex")

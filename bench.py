@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- point-clouds/sec of one BilateralConvFlex forward+backward (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--clouds B]
+
+Workload (BASELINE configs[1]): BilateralConvFlex(3, 1, 64, [64], splat+slice,
+norm, bias, LeakyReLU, last_relu=False) on FlyingThings3D-shaped frustum clouds of 8192 points,
+scale-1.0 lattice (in-lattice = out-lattice).  One *step* = forward+backward over a batch of B
+distinct clouds per GPU, concatenated into one launch sequence (the reference is B=1 only).
+Multi-GPU: clouds shard by sample, one process per GPU, no data-path collective (weak scaling).
+
+`value`  : clouds/s with inputs resident in HBM (CUDA events, max over ranks).
+`e2e`    : same metric through the module call with HOST (pinned) inputs: features + the index
+           tables the reference's DataLoader ships per sample are copied H2D every step, the
+           loss scalar and the parameter gradients are read back D2H.
+`--impl reference`: the reference's CPU algorithm (oracle/bcl.py port, torch CPU ops on all host
+           threads) on the same config, a bounded sample of clouds per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "point-clouds/sec (BCL fwd+bwd, 8192 pts, d=3, 64ch)"
+N_POINTS, CHANNELS, SCALE = 8192, 64, 1.0
+
+
+def measured_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def algorithmic_bytes(n, h, c, co, f=15, d1=4):
+    """bytes each stage must move once (fp32 values, 4-byte indices)."""
+    fwd = 4 * (n * c + 2 * d1 * n + h * c) + 4 * (h * c + f * h + f * c * co + co + h * co) + \
+        4 * (h * co + 2 * d1 * n + n * co)
+    bwd = 4 * (n * co + 2 * d1 * n + h * co) + 4 * (h * co + h * c + f * h + f * c * co) + \
+        4 * (h * c + f * c * co + co) + 4 * (h * c + 2 * d1 * n + h + n * c)
+    return fwd, bwd
+
+
+def blur_fwd_bytes(h, c, co, f=15):
+    return 4 * (h * c + f * h + f * c * co + co + h * co)
+
+
+def make_state(seed=0):
+    """Reference-format state_dict of the cfg2 module (default nn.Conv2d init under manual_seed)."""
+    import torch
+    import hplflownet_b200 as hpl
+    torch.manual_seed(seed)
+    mod = hpl.BilateralConvFlex(3, 1, CHANNELS, [CHANNELS], "cuda", use_bias=True, use_leaky=True,
+                                use_norm=True, do_splat=True, do_slice=True, last_relu=False, chunk_size=-1)
+    with torch.no_grad():
+        mod.bias.normal_(0, 0.1)
+    return mod
+
+
+def cloud_tables(seed):
+    """Index tables of one synthetic cloud (host tensors, reference format)."""
+    import torch
+    from hplflownet_b200.synthetic import frustum_pair
+    # TEMPORARY (first measurement only): tables come from the CPU oracle until the CUDA lattice
+    # builder lands; they are synthetic-input preparation outside every timed region.
+    from oracle import lattice as OL
+    pc1, pc2 = frustum_pair(N_POINTS, seed)
+    d = OL.generate(pc1, pc2, [[SCALE, 1, -1, -1]])[0]
+    return {k: (torch.from_numpy(v) if not isinstance(v, int) else v) for k, v in d.items()}
+
+
+# ------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's CPU implementation of the path (oracle port) on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import bcl as OB
+    from oracle import lattice as OL
+    from hplflownet_b200.synthetic import frustum_pair
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    mod = make_state()
+    state = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in mod.state_dict().items()}
+    clouds_per_step = 1
+    samples = []
+    for s in range(4):
+        pc1, pc2 = frustum_pair(N_POINTS, s)
+        d = OL.generate(pc1, pc2, [[SCALE, 1, -1, -1]])[0]
+        torch.manual_seed(s)
+        samples.append((torch.randn(1, CHANNELS, N_POINTS), torch.from_numpy(d["pc1_barycentric"])[None],
+                        torch.from_numpy(d["pc1_lattice_offset"])[None],
+                        torch.from_numpy(d["pc1_blur_neighbors"])[None], torch.randn(1, CHANNELS, N_POINTS),
+                        d["pc1_hash_cnt"]))
+
+    def step(i):
+        feat, bary, off, nbr, gy, _ = samples[i % len(samples)]
+        f = feat.clone().requires_grad_(True)
+        for v in state.values():
+            v.grad = None
+        y = OB.bcl_forward(state, f, bary, off, nbr, bary, off, do_splat=True, do_slice=True, use_norm=True,
+                           use_leaky=True, use_bias=True)
+        y.backward(gy)
+
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i)
+    dt = time.perf_counter() - t0
+    value = clouds_per_step * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BilateralConvFlex(3,1,64,[64]) fwd+bwd, 8192-pt frustum cloud, scale 1.0",
+                   "clouds_per_step": clouds_per_step, "H": [s[5] for s in samples]},
+        "cpu_baseline": {"value": value, "unit": "clouds/s", "cores": cores, "kind": "port",
+                         "sample": "%d steps x %d cloud (oracle/bcl.py, torch CPU ops, %d threads)"
+                                   % (args.steps, clouds_per_step, cores)},
+        "e2e": {"value": value, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import hplflownet_b200 as hpl
+    from hplflownet_b200 import _lib, ops
+    from hplflownet_b200.batching import concat_lattices
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.clouds
+
+    # ---- synthetic batch: B distinct clouds for this rank (weak scaling: B per GPU)
+    mod = make_state().to(dev)
+    items = [cloud_tables(rank * B + s) for s in range(B)]
+    batch = concat_lattices(items)
+    n_tot, h_tot = sum(batch["point_counts"]), sum(batch["vertex_counts"])
+    torch.manual_seed(1000 + rank)
+    host = {
+        "features": torch.randn(1, CHANNELS, n_tot).pin_memory(),
+        "barycentric": batch["barycentric"].pin_memory(),
+        "lattice_offset": batch["lattice_offset"].pin_memory(),
+        "blur_neighbors": batch["blur_neighbors"].pin_memory(),
+    }
+    gy = torch.randn(1, CHANNELS, n_tot, device=dev)
+    resident = {k: v.to(dev) for k, v in host.items()}
+    resident["features"].requires_grad_(True)
+    params = list(mod.parameters())
+
+    def fwd_bwd(t):
+        for p in params:
+            p.grad = None
+        t["features"].grad = None
+        y = mod(t["features"], t["barycentric"], t["lattice_offset"], t["blur_neighbors"],
+                t["barycentric"], t["lattice_offset"])
+        y.backward(gy)
+        return y
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident
+    for _ in range(args.warmup):
+        fwd_bwd(resident)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.PROFILE_GEMM = []
+    _lib.launch_count = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        fwd_bwd(resident)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count
+    gemm_events = ops.PROFILE_GEMM
+    ops.PROFILE_GEMM = None
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: host inputs, H2D inside the timed region, loss + parameter grads read back
+    def e2e_step():
+        t = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        t["features"].requires_grad_(True)
+        for p in params:
+            p.grad = None
+        y = mod(t["features"], t["barycentric"], t["lattice_offset"], t["blur_neighbors"],
+                t["barycentric"], t["lattice_offset"])
+        loss = (y * gy).sum()
+        loss.backward()
+        out = [loss.detach().cpu()] + [p.grad.cpu() for p in params]
+        return out
+
+    for _ in range(max(3, args.warmup // 2)):
+        e2e_step()
+    barrier()
+    e2e_steps = max(3, args.steps // 2)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = 4 + sum(p.numel() * 4 for p in params)
+
+    # ---- max over ranks
+    if world > 1:
+        tt = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, e2e_s = tt.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * B * args.steps / (ms * 1e-3)
+    e2e_value = world * B * e2e_steps / e2e_s
+
+    # ---- roofline of the dominant kernel (the blur gather-GEMM forward launch)
+    peaks = measured_peaks()
+    fwd_gemm = [a.elapsed_time(b) for tag, a, b in gemm_events if tag == "fwd"]
+    gemm_ms = sum(fwd_gemm) / max(1, len(fwd_gemm))
+    gemm_bytes = blur_fwd_bytes(h_tot, CHANNELS, CHANNELS)
+    gemm_flops = 2.0 * 15 * CHANNELS * CHANNELS * h_tot
+    achieved = gemm_bytes / (gemm_ms * 1e-3) / 1e9
+    fb, bb = algorithmic_bytes(n_tot, h_tot, CHANNELS, CHANNELS)
+    all_gemm_ms = sum(a.elapsed_time(b) for _, a, b in gemm_events) / args.steps
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+        "kernel": "gather_gemm_kernel (blur forward, fp32 CUDA-core FMA)",
+        "kernel_ms": gemm_ms, "kernel_tflops_fp32": gemm_flops / (gemm_ms * 1e-3) / 1e12,
+        "kernel_share_of_step": all_gemm_ms / (ms / args.steps),
+        "note": "compute-bound fp32 contraction (AI ~205 FLOP/B): the HBM fraction is low by construction; "
+                "kernel_tflops_fp32 vs ~74.5 TFLOP/s CUDA-core peak is the relevant ratio this round",
+        "whole_step_algorithmic_gbs": (fb + bb) / (ms / args.steps * 1e-3) / 1e9,
+    }
+
+    cpu = cpu_baseline_leg()
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BilateralConvFlex(3,1,64,[64]) fwd+bwd, 8192-pt frustum clouds, scale 1.0, "
+                               "%d distinct clouds per GPU per step concatenated (reference is B=1)" % B,
+                   "clouds_per_gpu_per_step": B, "points_per_step_per_gpu": n_tot, "vertices_per_step_per_gpu": h_tot,
+                   "l2_policy": "inputs larger than L2 (working set %.0f MB per step)" % (
+                       4e-6 * (2 * n_tot * CHANNELS + 2 * h_tot * CHANNELS)),
+                   "index_dtype": "int64 (reference format)"},
+        "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "clouds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline_leg():
+    """Oracle (port of the reference CPU path) timed on the host cores, bounded sample."""
+    import torch
+    from oracle import bcl as OB
+    from oracle import lattice as OL
+    from hplflownet_b200.synthetic import frustum_pair
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    mod = make_state()
+    state = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in mod.state_dict().items()}
+    n_clouds = 6
+    data = []
+    for s in range(n_clouds):
+        pc1, pc2 = frustum_pair(N_POINTS, s)
+        d = OL.generate(pc1, pc2, [[SCALE, 1, -1, -1]])[0]
+        torch.manual_seed(s)
+        data.append((torch.randn(1, CHANNELS, N_POINTS), torch.from_numpy(d["pc1_barycentric"])[None],
+                     torch.from_numpy(d["pc1_lattice_offset"])[None],
+                     torch.from_numpy(d["pc1_blur_neighbors"])[None], torch.randn(1, CHANNELS, N_POINTS)))
+
+    def one(i):
+        feat, bary, off, nbr, gy = data[i]
+        f = feat.clone().requires_grad_(True)
+        y = OB.bcl_forward(state, f, bary, off, nbr, bary, off, do_splat=True, do_slice=True, use_norm=True,
+                           use_leaky=True, use_bias=True)
+        y.backward(gy)
+
+    one(0)
+    t0 = time.perf_counter()
+    reps = 0
+    while reps < 3 * n_clouds and (time.perf_counter() - t0 < 12.0 or reps < n_clouds):
+        one(reps % n_clouds)
+        reps += 1
+    dt = time.perf_counter() - t0
+    return {"value": reps / dt, "unit": "clouds/s", "cores": cores, "kind": "port",
+            "sample": "%d clouds fwd+bwd in %.1f s (oracle/bcl.py, torch CPU, %d threads)" % (reps, dt, cores)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clouds", type=int, default=32, help="distinct clouds per GPU per step")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -31,6 +31,15 @@ SIGNATURES = {
 }
 
 
+# kernels enqueued per call (for bench.py's gpu_launches claim)
+LAUNCHES = {
+    "hpl_scatter_rows": 1, "hpl_normalize_rows": 2, "hpl_gather_rows": 1, "hpl_blur_gemm": 1,
+    "hpl_blur_wgrad": 2, "hpl_act_backward": 1, "hpl_transpose_table": 1, "hpl_cm_to_rows": 1,
+    "hpl_rows_to_cm": 1, "hpl_channel_sums": 1, "hpl_fill_zero": 1, "hpl_fill_i32": 1,
+}
+launch_count = 0
+
+
 class HplError(RuntimeError):
     pass
 
@@ -57,6 +66,8 @@ def load():
 
 def call(name, *args):
     """Invoke an ABI entry point; raise HplError on a non-zero return code."""
+    global launch_count
+    launch_count += LAUNCHES.get(name, 0)
     rc = getattr(load(), name)(*args)
     if rc != 0:
         detail = "argument error" if rc < 0 else "CUDA error %d" % rc

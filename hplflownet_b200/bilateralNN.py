@@ -62,7 +62,6 @@ class _BCLFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg, features, in_bary, in_off, nbr, out_bary, out_off, slice_bias, *params):
         do_splat, do_slice, use_norm, acts = cfg
-        dev = features.device
         feat = features[0].contiguous()                      # (C, N) -- B = 1 (README.md:57)
         c_in = feat.size(0)
         nbr2 = nbr[0].contiguous()                           # (F, H)
@@ -141,7 +140,7 @@ class _BCLFunction(torch.autograd.Function):
             if l > 0 or need_feat:
                 wd = wts[l].transpose(1, 2).contiguous()                           # (F, Co, C)
                 tbl_t = ops.transpose_table(nbr2, h) if l == 0 else None
-                dx = ops.blur_gemm(dx, chans[l + 1], tbl_t, h, wd, None, ops.ACT_NONE)
+                dx = ops.blur_gemm(dx, chans[l + 1], tbl_t, h, wd, None, ops.ACT_NONE, tag="dgrad")
 
         d_feat = None
         if need_feat:

@@ -10,6 +10,26 @@ from . import _lib
 
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 
+# bench.py sets this to a list to collect (tag, start_event, end_event) around the contraction
+# kernels (CUDA events on the launching stream); None = no instrumentation.
+PROFILE_GEMM = None
+
+
+class _timed:
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        if PROFILE_GEMM is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if PROFILE_GEMM is not None:
+            self.e1.record()
+            PROFILE_GEMM.append((self.tag, self.e0, self.e1))
+
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
@@ -70,7 +90,8 @@ def gather_rows(rows, channels, bary, off, scale=None, bias=None):
     return y
 
 
-def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_major=False, precision=0):
+def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_major=False, precision=0,
+              tag="fwd"):
     """out[v] = act(bias + sum_f x[nbr[f, v]] @ w[f]);  w (F, C, Co)."""
     _f32(x, "x"); _f32(w, "w")
     f, c, co = w.shape
@@ -85,9 +106,10 @@ def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_majo
     if out is None:
         out = (torch.empty((co, n_out_rows), dtype=torch.float32, device=x.device) if out_channel_major
                else alloc_rows(n_out_rows, co, x.device))
-    _lib.call("hpl_blur_gemm", x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, f, n_out_rows, c, co,
-              w.data_ptr(), bias.data_ptr() if bias is not None else None, act, out.data_ptr(),
-              out.stride(0), int(out_channel_major), precision, _stream())
+    with _timed(tag):
+        _lib.call("hpl_blur_gemm", x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, f, n_out_rows, c, co,
+                  w.data_ptr(), bias.data_ptr() if bias is not None else None, act, out.data_ptr(),
+                  out.stride(0), int(out_channel_major), precision, _stream())
     return out
 
 
@@ -101,9 +123,10 @@ def blur_wgrad(x, c_in, nbr, n_out_rows, dz, c_out, filter_size, want_db=True):
         nbr_ptr, i64 = None, 0
     dw = torch.zeros((filter_size, c_in, c_out), dtype=torch.float32, device=x.device)
     db = torch.zeros(c_out, dtype=torch.float32, device=x.device) if want_db else None
-    _lib.call("hpl_blur_wgrad", x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, filter_size, n_out_rows,
-              c_in, c_out, dz.data_ptr(), dz.stride(0), dw.data_ptr(), db.data_ptr() if want_db else None,
-              _stream())
+    with _timed("wgrad"):
+        _lib.call("hpl_blur_wgrad", x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, filter_size, n_out_rows,
+                  c_in, c_out, dz.data_ptr(), dz.stride(0), dw.data_ptr(), db.data_ptr() if want_db else None,
+                  _stream())
     return dw, db
 
 

@@ -110,16 +110,23 @@ def make_state(seed=0):
     return mod
 
 
+_GEN = None
+
+
 def cloud_tables(seed):
-    """Index tables of one synthetic cloud (host tensors, reference format)."""
-    import torch
+    """Index tables of one synthetic cloud, built by the CUDA lattice builder (product path),
+    returned as HOST tensors in the reference's format (int64) -- what its DataLoader delivers."""
+    global _GEN
     from hplflownet_b200.synthetic import frustum_pair
-    # TEMPORARY (first measurement only): tables come from the CPU oracle until the CUDA lattice
-    # builder lands; they are synthetic-input preparation outside every timed region.
-    from oracle import lattice as OL
+    from hplflownet_b200.transforms import GenerateDataUnsymmetric
+    if _GEN is None:
+        class A:
+            dim = 3
+            scales_filter_map = [[SCALE, 1, -1, -1]]
+        _GEN = GenerateDataUnsymmetric(A())
     pc1, pc2 = frustum_pair(N_POINTS, seed)
-    d = OL.generate(pc1, pc2, [[SCALE, 1, -1, -1]])[0]
-    return {k: (torch.from_numpy(v) if not isinstance(v, int) else v) for k, v in d.items()}
+    d = _GEN([pc1, pc2, pc1])[3][0]
+    return {k: (v.cpu() if not isinstance(v, int) else v) for k, v in d.items()}
 
 
 # ------------------------------------------------------------------------------ reference arm

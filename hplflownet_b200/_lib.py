@@ -26,16 +26,28 @@ SIGNATURES = {
     "hpl_cm_to_rows": [vp, i64, i64, i64, vp, i64, vp],
     "hpl_rows_to_cm": [vp, i64, i64, i64, vp, i64, vp],
     "hpl_channel_sums": [vp, i64, i64, vp, vp],
+    "hpl_lattice_init_range": [vp, vp],
+    "hpl_lattice_points": [vp, i64, ctypes.c_float, vp, vp, vp, vp, vp, vp],
+    "hpl_lattice_table_capacity": [i64],
+    "hpl_lattice_scan_blocks": [i64],
+    "hpl_lattice_insert": [vp, vp, i64, vp, vp, vp, vp, i64, vp, vp, vp, cint, vp, vp, vp],
+    "hpl_lattice_neighbors": [vp, vp, i64, vp, vp, vp, i64, vp, i64, vp, cint, i64, vp],
+    "hpl_lattice_corr_table": [vp, vp, i64, vp, vp, vp, i64, vp, i64, vp, i64, vp, cint, i64, vp],
+    "hpl_lattice_next_points": [vp, i64, ctypes.c_float, vp, vp],
     "hpl_fill_zero": [vp, i64, vp],
     "hpl_fill_i32": [vp, i64, i32, vp],
 }
 
+
+RETURNS_I64 = {"hpl_lattice_table_capacity", "hpl_lattice_scan_blocks"}   # sizes, not status codes
 
 # kernels enqueued per call (for bench.py's gpu_launches claim)
 LAUNCHES = {
     "hpl_scatter_rows": 1, "hpl_normalize_rows": 2, "hpl_gather_rows": 1, "hpl_blur_gemm": 1,
     "hpl_blur_wgrad": 2, "hpl_act_backward": 1, "hpl_transpose_table": 1, "hpl_cm_to_rows": 1,
     "hpl_rows_to_cm": 1, "hpl_channel_sums": 1, "hpl_fill_zero": 1, "hpl_fill_i32": 1,
+    "hpl_lattice_init_range": 1, "hpl_lattice_points": 1, "hpl_lattice_insert": 6,
+    "hpl_lattice_neighbors": 1, "hpl_lattice_corr_table": 1, "hpl_lattice_next_points": 1,
 }
 launch_count = 0
 
@@ -59,7 +71,7 @@ def load():
         for name, args in SIGNATURES.items():
             fn = getattr(lib, name)          # AttributeError if the .so is stale
             fn.argtypes = args
-            fn.restype = cint
+            fn.restype = i64 if name in RETURNS_I64 else cint
         _lib = lib
     return _lib
 

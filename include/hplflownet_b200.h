@@ -116,6 +116,65 @@ int hpl_rows_to_cm(const float* rows, int64_t ld, int64_t n, int64_t channels, f
 /* sums[c] += sum_n x[c, n]   (bias gradient of SLICE, bilateralNN.py:235-236). x (C, N). */
 int hpl_channel_sums(const float* x, int64_t channels, int64_t n, float* sums, void* stream);
 
+/* ---------------------------------------------------------------- index half
+ * GPU replacement of GenerateDataUnsymmetric + build_unsymmetric + khash
+ * (transforms/transforms.py:133-261,264-485; models/khash_int2int.h:8-33).  All results are
+ * bit-exact with the reference (vertex ids = first-occurrence order of a point-outer /
+ * remainder-inner scan, transforms.py:179-192).  One call sequence per scale:
+ *   hpl_lattice_init_range(range)                       once per cloud pair
+ *   hpl_lattice_points(cloud 1), hpl_lattice_points(cloud 2)       fold both key ranges (:384-385)
+ *   hpl_lattice_insert(cloud 1), hpl_lattice_insert(cloud 2)       hash build, ids, lattice_offset
+ *   hpl_lattice_neighbors / hpl_lattice_corr_table                  blur and correlation tables
+ *   hpl_lattice_next_points                                         input points of the next scale
+ * The khash table (void* handle, get/set per key through cffi) becomes three flat device arrays
+ * owned by the caller: table_keys (cap uint64), table_first (cap int32), table_ids (cap int32). */
+
+/* key_minmax[0..3] = INT_MAX, [4..7] = INT_MIN. */
+int hpl_lattice_init_range(int32_t* key_minmax, void* stream);
+
+/* get_keys_and_barycentric (transforms.py:300-353) for pc * scale (:377).  pc (3, N) fp32.
+ * Outputs: bary (4, N), el_minus_gr (4, N) fp32; greedy (N, 4) int32 = rounded remainder-0
+ * point; rankpack (N) = the 4 ranks, one byte each (together they encode the (4, N, 4) int64
+ * key tensor of the reference); key_minmax is folded with this cloud's per-coordinate range. */
+int hpl_lattice_points(const float* pc, int64_t n_points, float scale, float* bary, float* el_minus_gr,
+                       int32_t* greedy, uint32_t* rankpack, int32_t* key_minmax, void* stream);
+
+/* Hash-table capacity (power of two >= 8 N) and scan workspace length (int32) for N points. */
+int64_t hpl_lattice_table_capacity(int64_t n_points);
+int64_t hpl_lattice_scan_blocks(int64_t n_points);
+
+/* build_unsymmetric hot loop 1 (transforms.py:179-207), khash_get/set (khash_int2int.h:17-33):
+ * insert the packed key (key2int, :70-86) of every (point, remainder), number the distinct
+ * keys in first-occurrence order, write lattice_offset (4, N) (int64 if idx64 else int32),
+ * vertex_coords (>= 4N capacity, 4) int32 = key of each vertex in id order (the reference's
+ * last_pc, :188-189) and *n_vertices (device int32) = H (:387-391).
+ * slot_of (4N int32) and scan_ws (hpl_lattice_scan_blocks ints) are workspace. */
+int hpl_lattice_insert(const int32_t* greedy, const uint32_t* rankpack, int64_t n_points,
+                       const int32_t* key_minmax, uint64_t* table_keys, int32_t* table_first,
+                       int32_t* table_ids, int64_t table_cap, int32_t* slot_of, int32_t* scan_ws,
+                       void* lattice_offset, int idx64, int32_t* vertex_coords, int32_t* n_vertices,
+                       void* stream);
+
+/* Hot loops 2 and 4 (transforms.py:209-221,243-255): out[f, h] = id of key_h + offsets[f] in
+ * the given table, or -1.  offsets (F, 4) int32 device.  out (F, ld). h_cap = rows to fill. */
+int hpl_lattice_neighbors(const int32_t* vertex_coords, const int32_t* n_vertices, int64_t h_cap,
+                          const int32_t* key_minmax, const uint64_t* table_keys,
+                          const int32_t* table_ids, int64_t table_cap, const int32_t* offsets,
+                          int64_t filter_size, void* out, int idx64, int64_t ld, void* stream);
+
+/* Hot loop 3 (transforms.py:223-241): out[f, p, h] = id IN TABLE 2 of
+ * key1_h + corr_offsets[p] + filter_offsets[f], or -1.  out (F*P, ld). */
+int hpl_lattice_corr_table(const int32_t* vertex_coords1, const int32_t* n_vertices1, int64_t h_cap,
+                           const int32_t* key_minmax, const uint64_t* table_keys2,
+                           const int32_t* table_ids2, int64_t table_cap2, const int32_t* corr_offsets,
+                           int64_t corr_size, const int32_t* filter_offsets, int64_t filter_size,
+                           void* out, int idx64, int64_t ld, void* stream);
+
+/* transforms.py:461-467: out (3, H) = E^T . (vertex_coords / divisor), divisor =
+ * fp32(expected_std * scale); true division, k-ordered FMA chain. */
+int hpl_lattice_next_points(const int32_t* vertex_coords, int64_t n_vertices, float divisor,
+                            float* out, void* stream);
+
 int hpl_fill_zero(void* ptr, int64_t bytes, void* stream);
 int hpl_fill_i32(int32_t* ptr, int64_t count, int32_t value, void* stream);
 

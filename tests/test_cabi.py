@@ -65,3 +65,12 @@ def test_cpu_tensors_are_rejected_loudly():
     x = torch.zeros(1, 4, 8)
     with pytest.raises(RuntimeError, match="no CPU path"):
         mod(x, None, None, torch.zeros(1, 15, 3, dtype=torch.long), None, None)
+
+
+def test_neighbor_offsets_match_reference_order():
+    # Traverse.go order for r=1 (conv-weight index f <-> offset f), and vs the oracle for r=2
+    from hplflownet_b200.transforms import filter_size, neighbor_offsets
+    from oracle import lattice as OL
+    assert filter_size(1) == 15
+    for r in (1, 2, 3):
+        assert (neighbor_offsets(r) == OL.neighbor_offsets(r)).all()

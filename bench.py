@@ -314,6 +314,7 @@ def run_ours(args):
     }
 
     cpu = cpu_baseline_leg()
+    lattice = lattice_leg(dev)
 
     line = {
         "metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": world, "steps": args.steps,
@@ -328,11 +329,45 @@ def run_ours(args):
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "clouds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps},
-        "gpu_launches": launches, "clocks": clocks,
+        "gpu_launches": launches, "clocks": clocks, "lattice_build": lattice,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def lattice_leg(dev):
+    """Secondary number: the index half (GenerateDataUnsymmetric, 7-scale hierarchy of the
+    reference's configs) on the GPU vs the oracle's C restatement on one host core."""
+    import torch
+    from hplflownet_b200.synthetic import frustum_pair
+    from hplflownet_b200.transforms import GenerateDataUnsymmetric
+    from oracle import lattice as OL
+
+    class A:
+        dim = 3
+        scales_filter_map = [[3., 1, -1, -1], [2., 1, -1, -1], [1., 1, 1, 1], [.5, 1, 1, 1], [.25, 1, 1, 1],
+                             [.125, 1, 1, 1], [.0625, 1, 1, 1]]
+    gen = GenerateDataUnsymmetric(A(), device=dev, index_dtype=torch.int32)
+    pairs = [frustum_pair(N_POINTS, 100 + s) for s in range(4)]
+    dev_pairs = [(torch.from_numpy(a.T.copy()).to(dev), torch.from_numpy(b.T.copy()).to(dev)) for a, b in pairs]
+    for a, b in dev_pairs[:2]:
+        gen.build(a, b)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 12
+    for i in range(reps):
+        a, b = dev_pairs[i % len(dev_pairs)]
+        gen.build(a, b)
+    torch.cuda.synchronize()
+    gpu = reps / (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    for a, b in pairs[:2]:
+        OL.generate(a, b, A.scales_filter_map)
+    cpu = 2 / (time.perf_counter() - t0)
+    return {"workload": "7-scale lattice hierarchy of one 8192+8192-pt pair (configs/test_ours_FlyingThings3D.yaml)",
+            "value": gpu, "unit": "pairs/s", "cpu_port_value": cpu, "cpu_port_cores": 1,
+            "note": "wall clock incl. one host sync per scale; reference Numba/khash build: 4.1-4.9 s/pair (SURVEY §6)"}
 
 
 def cpu_baseline_leg():

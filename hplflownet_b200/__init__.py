@@ -6,6 +6,7 @@ and the lattice builder ``GenerateDataUnsymmetric`` (transforms/transforms.py), 
 hand-written CUDA behind the C ABI in include/hplflownet_b200.h.  No CPU fallback.
 """
 from .bilateralNN import BilateralConvFlex, SparseSum, sparse_sum  # noqa: F401
+from .bnn_flow import BilateralCorrelationFlex  # noqa: F401
 from .module_utils import Conv1dReLU, Conv2dReLU, Conv3dReLU  # noqa: F401
 
 __version__ = "0.1.0"

@@ -21,11 +21,14 @@ SIGNATURES = {
     "hpl_gather_rows": [vp, i64, vp, vp, cint, vp, vp, i64, i64, vp, vp],
     "hpl_blur_gemm": [vp, i64, i64, vp, cint, i64, i64, i64, i64, vp, vp, cint, vp, i64, cint, cint, vp],
     "hpl_blur_wgrad": [vp, i64, i64, vp, cint, i64, i64, i64, i64, vp, i64, vp, vp, vp],
+    "hpl_column_sums": [vp, i64, i64, i64, vp, vp],
     "hpl_act_backward": [vp, i64, vp, i64, i64, i64, cint, vp],
     "hpl_transpose_table": [vp, cint, i64, i64, vp, i64, vp, vp],
     "hpl_cm_to_rows": [vp, i64, i64, i64, vp, i64, vp],
     "hpl_rows_to_cm": [vp, i64, i64, i64, vp, i64, vp],
     "hpl_channel_sums": [vp, i64, i64, vp, vp],
+    "hpl_corr_gather": [vp, i64, vp, vp, i64, vp, cint, vp, cint, vp, i64, i64, i64, i64, i64, vp],
+    "hpl_corr_scatter": [vp, i64, vp, vp, cint, vp, i64, vp, i64, i64, i64, i64, i64, vp],
     "hpl_lattice_init_range": [vp, vp],
     "hpl_lattice_points": [vp, i64, ctypes.c_float, vp, vp, vp, vp, vp, vp],
     "hpl_lattice_table_capacity": [i64],
@@ -46,6 +49,7 @@ LAUNCHES = {
     "hpl_scatter_rows": 1, "hpl_normalize_rows": 2, "hpl_gather_rows": 1, "hpl_blur_gemm": 1,
     "hpl_blur_wgrad": 2, "hpl_act_backward": 1, "hpl_transpose_table": 1, "hpl_cm_to_rows": 1,
     "hpl_rows_to_cm": 1, "hpl_channel_sums": 1, "hpl_fill_zero": 1, "hpl_fill_i32": 1,
+    "hpl_corr_gather": 1, "hpl_corr_scatter": 1, "hpl_column_sums": 1,
     "hpl_lattice_init_range": 1, "hpl_lattice_points": 1, "hpl_lattice_insert": 6,
     "hpl_lattice_neighbors": 1, "hpl_lattice_corr_table": 1, "hpl_lattice_next_points": 1,
 }

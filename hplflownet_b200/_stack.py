@@ -1,0 +1,47 @@
+"""A stack of learned lattice convolutions (gather-GEMM + bias + activation) and its backward.
+
+Shared by BilateralConvFlex (blur_conv, models/bilateralNN.py:94-113) and
+BilateralCorrelationFlex (corr_conv / blur_conv, models/bnn_flow.py:59-91).  Each layer is
+``(w (F, C, Co) fp32, bias (Co) or None, act)``; only the first layer may carry a neighbour table.
+"""
+from . import ops
+
+
+def forward(x, c_in, n_rows, layers, first_nbr=None, last_channel_major=False):
+    """Returns (xs, chans, out_cm): xs[l] is the vertex-major input of layer l and xs[-1] the final
+    vertex-major output -- unless the last layer is written channel-major directly (only when it has
+    no activation), in which case it is returned as out_cm and not kept in xs."""
+    xs, chans, out_cm = [x], [c_in], None
+    for l, (w, b, act) in enumerate(layers):
+        last = l == len(layers) - 1
+        direct_cm = last and last_channel_major and act == ops.ACT_NONE
+        y = ops.blur_gemm(xs[-1], chans[-1], first_nbr if l == 0 else None, n_rows, w, b,
+                          act, out_channel_major=direct_cm)
+        if direct_cm:
+            out_cm = y
+        else:
+            xs.append(y)
+        chans.append(w.size(2))
+    return xs, chans, out_cm
+
+
+def backward(dx, xs, chans, layers, n_rows, first_nbr, first_nbr_t, need_input_grad, need_param_grad):
+    """dx: gradient w.r.t. the stack's (post-activation) output, vertex-major, modified in place.
+    first_nbr_t: callable returning the transposed table of the first layer (built lazily).
+    Returns (dx_in or None, [(dw (F, C, Co), db (Co)) or None per layer])."""
+    grads = [None] * len(layers)
+    for l in range(len(layers) - 1, -1, -1):
+        w, b, act = layers[l]
+        if act != ops.ACT_NONE:
+            ops.act_backward_(dx, xs[l + 1], chans[l + 1], act)
+        tbl = first_nbr if l == 0 else None
+        if need_param_grad[l]:
+            grads[l] = ops.blur_wgrad(xs[l], chans[l], tbl, n_rows, dx, chans[l + 1], w.size(0), want_db=b is not None)
+        if l > 0 or need_input_grad:
+            wd = w.transpose(1, 2).contiguous()                       # (F, Co, C)
+            tbl_t = first_nbr_t() if (l == 0 and first_nbr is not None) else None
+            n_in = xs[l].size(0)
+            dx = ops.blur_gemm(dx, chans[l + 1], tbl_t, n_in, wd, None, ops.ACT_NONE, tag="dgrad")
+        else:
+            dx = None
+    return dx, grads

@@ -16,7 +16,7 @@ kernel.  There is no CPU path: tensors must live on a CUDA device.
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import _stack, ops
 from .module_utils import Conv2dReLU
 
 __all__ = ["BilateralConvFlex", "SparseSum", "sparse_sum"]
@@ -56,6 +56,25 @@ class SparseSum(torch.autograd.Function):
 sparse_sum = SparseSum.apply
 
 
+def conv2d_layers(module_list, use_leaky):
+    """[(conv, act_code)] for a reference-layout Sequential of Conv2dReLU / bare nn.Conv2d."""
+    out = []
+    for layer in module_list:
+        has_act = isinstance(layer, Conv2dReLU)
+        out.append((layer.conv if has_act else layer, _act_code(has_act, use_leaky)))
+    return out
+
+
+def kernel_weight(w):
+    """(Co, C, F, 1) conv weight -> (F, C, Co) contiguous operand of hpl_blur_gemm."""
+    return w.detach().reshape(w.size(0), w.size(1), -1).permute(2, 1, 0).contiguous()
+
+
+def conv_weight_grad(dw, like):
+    """(F, C, Co) -> the conv weight's own shape."""
+    return dw.permute(2, 1, 0).reshape(tuple(like)).contiguous()
+
+
 class _BCLFunction(torch.autograd.Function):
     """splat -> conv stack -> slice with a hand-written backward (autograd in the reference)."""
 
@@ -65,7 +84,7 @@ class _BCLFunction(torch.autograd.Function):
         feat = features[0].contiguous()                      # (C, N) -- B = 1 (README.md:57)
         c_in = feat.size(0)
         nbr2 = nbr[0].contiguous()                           # (F, H)
-        filter_size, h = nbr2.shape
+        h = nbr2.size(1)
         inv = None
         if do_splat:
             bary_i, off_i = in_bary[0].contiguous(), in_off[0].contiguous()
@@ -76,47 +95,29 @@ class _BCLFunction(torch.autograd.Function):
             bary_i = off_i = None
             lat = ops.cm_to_rows(feat)
 
-        n_layers = len(params) // 2
-        xs = [lat]                                           # xs[l] = input of layer l (vertex-major)
-        chans = [c_in]
-        wts = []
-        x = lat
-        y_cm = None
-        for l in range(n_layers):
-            w, b = params[2 * l], params[2 * l + 1]
-            wt = w.detach()[:, :, :, 0].permute(2, 1, 0).contiguous()    # (F or 1, C, Co)
-            wts.append(wt)
-            co = wt.size(2)
-            last = l == n_layers - 1
-            direct_cm = last and not do_slice and acts[l] == ops.ACT_NONE
-            x = ops.blur_gemm(x, chans[-1], nbr2 if l == 0 else None, h, wt, b.detach(), acts[l],
-                              out_channel_major=direct_cm)
-            if direct_cm:
-                y_cm = x
-            else:
-                xs.append(x)
-            chans.append(co)
+        layers = [(kernel_weight(params[2 * l]), params[2 * l + 1].detach(), acts[l]) for l in range(len(acts))]
+        xs, chans, out_cm = _stack.forward(lat, c_in, h, layers, nbr2, last_channel_major=not do_slice)
 
         if do_slice:
             bary_o, off_o = out_bary[0].contiguous(), out_off[0].contiguous()
-            out = ops.gather_rows(x, chans[-1], bary_o, off_o, None,
+            out = ops.gather_rows(xs[-1], chans[-1], bary_o, off_o, None,
                                   slice_bias.detach() if slice_bias is not None else None)
         else:
             bary_o = off_o = None
-            out = y_cm if y_cm is not None else ops.rows_to_cm(x, chans[-1])
+            out = out_cm if out_cm is not None else ops.rows_to_cm(xs[-1], chans[-1])
 
-        ctx.cfg, ctx.chans, ctx.h, ctx.filter_size = cfg, chans, h, filter_size
-        ctx.xs, ctx.wts, ctx.inv = xs, wts, inv
+        ctx.cfg, ctx.chans, ctx.h = cfg, chans, h
+        ctx.xs, ctx.layers, ctx.inv = xs, layers, inv
         ctx.idx = (bary_i, off_i, nbr2, bary_o, off_o)
         ctx.has_slice_bias = slice_bias is not None
+        ctx.param_shapes = [p.shape for p in params]
         return out.unsqueeze(0)
 
     @staticmethod
     def backward(ctx, grad_out):
         do_splat, do_slice, use_norm, acts = ctx.cfg
         bary_i, off_i, nbr2, bary_o, off_o = ctx.idx
-        chans, h, xs, wts = ctx.chans, ctx.h, ctx.xs, ctx.wts
-        n_layers = len(wts)
+        chans, h, xs, layers = ctx.chans, ctx.h, ctx.xs, ctx.layers
         g = grad_out[0].contiguous()
         d_slice_bias = None
         if do_slice:
@@ -126,21 +127,16 @@ class _BCLFunction(torch.autograd.Function):
         else:
             dx = ops.cm_to_rows(g)
 
-        grads = [None] * (2 * n_layers)
         need_feat = ctx.needs_input_grad[1]
-        for l in range(n_layers - 1, -1, -1):
-            if acts[l] != ops.ACT_NONE:
-                ops.act_backward_(dx, xs[l + 1], chans[l + 1], acts[l])
-            tbl = nbr2 if l == 0 else None
-            fs = ctx.filter_size if l == 0 else 1
-            if ctx.needs_input_grad[8 + 2 * l] or ctx.needs_input_grad[9 + 2 * l]:
-                dw, db = ops.blur_wgrad(xs[l], chans[l], tbl, h, dx, chans[l + 1], fs)
-                grads[2 * l] = dw.permute(2, 1, 0).unsqueeze(-1).contiguous()      # (Co, C, F, 1)
-                grads[2 * l + 1] = db
-            if l > 0 or need_feat:
-                wd = wts[l].transpose(1, 2).contiguous()                           # (F, Co, C)
-                tbl_t = ops.transpose_table(nbr2, h) if l == 0 else None
-                dx = ops.blur_gemm(dx, chans[l + 1], tbl_t, h, wd, None, ops.ACT_NONE, tag="dgrad")
+        need_param = [ctx.needs_input_grad[8 + 2 * l] or ctx.needs_input_grad[9 + 2 * l] for l in range(len(layers))]
+        dx, pg = _stack.backward(dx, xs, chans, layers, h, nbr2, lambda: ops.transpose_table(nbr2, h),
+                                 need_feat, need_param)
+        grads = []
+        for l, g_l in enumerate(pg):
+            if g_l is None:
+                grads += [None, None]
+            else:
+                grads += [conv_weight_grad(g_l[0], ctx.param_shapes[2 * l]), g_l[1]]
 
         d_feat = None
         if need_feat:
@@ -192,10 +188,9 @@ class BilateralConvFlex(nn.Module):
 
     def _layer_params(self):
         params, acts = [], []
-        for layer in self.blur_conv:
-            conv = layer.conv if isinstance(layer, Conv2dReLU) else layer
+        for conv, act in conv2d_layers(self.blur_conv, self.use_leaky):
             params += [conv.weight, conv.bias]
-            acts.append(_act_code(isinstance(layer, Conv2dReLU), self.use_leaky))
+            acts.append(act)
         return params, tuple(acts)
 
     def forward(self, features, in_barycentric, in_lattice_offset, blur_neighbors, out_barycentric,

@@ -285,6 +285,17 @@ int hpl_blur_gemm(const float* in, int64_t ld_in, int64_t n_in_rows, const void*
     HPL_RETURN_LAST();
 }
 
+int hpl_column_sums(const float* rows, int64_t ld, int64_t n_rows, int64_t channels, float* sums, void* stream) {
+    HPL_CHECK_ARG(rows && sums && ld >= channels && channels > 0);
+    if (n_rows == 0) return 0;
+    long long blocks_y = (n_rows + 511) / 512;
+    if (blocks_y > 1024) blocks_y = 1024;
+    const long long rpb = (n_rows + blocks_y - 1) / blocks_y;
+    dim3 g2((unsigned)((channels + 63) / 64), (unsigned)blocks_y);
+    column_sums_kernel<<<g2, 64, 0, as_stream(stream)>>>(rows, ld, n_rows, (int)channels, sums, rpb);
+    HPL_RETURN_LAST();
+}
+
 int hpl_blur_wgrad(const float* in, int64_t ld_in, int64_t n_in_rows, const void* nbr, int idx64,
                    int64_t filter_size, int64_t n_out_rows, int64_t c_in, int64_t c_out, const float* dz,
                    int64_t ld_dz, float* dw, float* db, void* stream) {
@@ -310,13 +321,7 @@ int hpl_blur_wgrad(const float* in, int64_t ld_in, int64_t n_in_rows, const void
     else
         wgrad_kernel<false><<<grid, kWgradThreads, 0, as_stream(stream)>>>(in, ld_in, n_in_rows, nbr, n_out_rows, (int)c_in,
                                                                            (int)c_out, dz, ld_dz, dw, tiles_n, rows_per_split);
-    if (db != nullptr) {
-        long long blocks_y = (n_out_rows + 511) / 512;
-        if (blocks_y > 1024) blocks_y = 1024;
-        const long long rpb = (n_out_rows + blocks_y - 1) / blocks_y;
-        dim3 g2((unsigned)((c_out + 63) / 64), (unsigned)blocks_y);
-        column_sums_kernel<<<g2, 64, 0, as_stream(stream)>>>(dz, ld_dz, n_out_rows, (int)c_out, db, rpb);
-    }
+    if (db != nullptr) return hpl_column_sums(dz, ld_dz, n_out_rows, c_out, db, stream);
     HPL_RETURN_LAST();
 }
 

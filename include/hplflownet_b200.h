@@ -93,6 +93,10 @@ int hpl_blur_wgrad(const float* in, int64_t ld_in, int64_t n_in_rows, const void
                    int64_t filter_size, int64_t n_out_rows, int64_t c_in, int64_t c_out,
                    const float* dz, int64_t ld_dz, float* dw, float* db, void* stream);
 
+/* sums[c] += sum_v rows[v, c]  (conv bias gradients). rows (n_rows, ld) vertex-major. */
+int hpl_column_sums(const float* rows, int64_t ld, int64_t n_rows, int64_t channels, float* sums,
+                    void* stream);
+
 /* Activation backward, in place:  dz[v, c] *= (y[v, c] > 0 ? 1 : slope(act)).
  * LeakyReLU/ReLU keep the sign, so the saved output is enough (module_utils.py:34). */
 int hpl_act_backward(float* dz, int64_t ld_dz, const float* y, int64_t ld_y, int64_t n_rows,
@@ -115,6 +119,24 @@ int hpl_rows_to_cm(const float* rows, int64_t ld, int64_t n, int64_t channels, f
 
 /* sums[c] += sum_n x[c, n]   (bias gradient of SLICE, bilateralNN.py:235-236). x (C, N). */
 int hpl_channel_sums(const float* x, int64_t channels, int64_t n, float* sums, void* stream);
+
+/* Patch-correlation stage of BilateralCorrelationFlex (bnn_flow.py:189-202).  The first
+ * Conv3d (1,P,1) layer is applied per SOURCE vertex and patch slot with two dense GEMMs
+ * (hpl_blur_gemm, nbr = NULL) giving t1 (H1, P*width) and t2 (H2, P*width); this call then forms
+ *   z[v*F + f, :] = act(bias + sum_p t1[i1[p,v], p*width:(p+1)*width]
+ *                            + sum_p t2[i2[f,p,v], p*width:(p+1)*width])
+ * i1 (P, H1) = pc1_corr_indices, i2 (F, P, H1) = pc2_corr_indices, -1 reads zeros.
+ * z (H1*F, ldz): row v*F+f, so the same memory is the (H1, F*ldz) operand of the displacement
+ * filter (:205).  width % 4 == 0. */
+int hpl_corr_gather(const float* t1, int64_t ld1, const void* i1, const float* t2, int64_t ld2,
+                    const void* i2, int idx64, const float* bias, int act, float* z, int64_t ldz,
+                    int64_t width, int64_t patch, int64_t filt, int64_t h1, void* stream);
+
+/* Backward of hpl_corr_gather w.r.t. t1 and t2 (fp32 RED into zeroed dt1 / dt2):
+ *   dt2[i2[f,p,v], p, :] += dz[v*F+f, :]      dt1[i1[p,v], p, :] += sum_f dz[v*F+f, :] */
+int hpl_corr_scatter(const float* dz, int64_t ldz, const void* i1, const void* i2, int idx64,
+                     float* dt1, int64_t ld1, float* dt2, int64_t ld2, int64_t width, int64_t patch,
+                     int64_t filt, int64_t h1, void* stream);
 
 /* ---------------------------------------------------------------- index half
  * GPU replacement of GenerateDataUnsymmetric + build_unsymmetric + khash

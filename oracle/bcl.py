@@ -16,8 +16,12 @@ against outputs and gradients dumped from the unmodified reference modules
 (oracle/make_golden.py), tests/test_oracle_vs_reference.py re-checks live when
 /root/reference is importable.
 """
+import warnings
+
 import torch
 import torch.nn.functional as F
+
+warnings.filterwarnings("ignore", message="Sparse invariant checks are implicitly disabled")
 
 LEAKY_RATE = 0.1  # models/module_utils.py:6
 
@@ -66,7 +70,7 @@ def splat(features, barycentric, lattice_offset, n_vertices, use_norm):
 
 def _pad_null(features):
     """bilateralNN.py:190-196: prepend the null-vertex column."""
-    z = torch.zeros((features.size(0), features.size(1), 1), dtype=features.dtype)
+    z = torch.zeros((features.size(0), features.size(1), 1), dtype=features.dtype, device=features.device)
     return torch.cat((z, features), dim=-1)
 
 

@@ -74,3 +74,19 @@ def test_neighbor_offsets_match_reference_order():
     assert filter_size(1) == 15
     for r in (1, 2, 3):
         assert (neighbor_offsets(r) == OL.neighbor_offsets(r)).all()
+
+
+@pytest.mark.parametrize("name", golden_files("corr_"))
+def test_corr_state_dict_layout_matches_reference(name):
+    g = golden(name)
+    c, prev_dim, use_leaky, last_relu = [int(x) for x in g["cfg"]]
+    mod = hpl.BilateralCorrelationFlex(3, 1, 1, c, [int(x) for x in g["corr_out"]], [int(x) for x in g["out_ch"]],
+                                       "cuda", use_bias=True, use_leaky=bool(use_leaky), use_norm=True,
+                                       prev_corr_dim=prev_dim, last_relu=bool(last_relu), chunk_size=-1)
+    ref_state = state_from(g)
+    mine = mod.state_dict()
+    assert sorted(mine) == sorted(ref_state)
+    for k in mine:
+        assert mine[k].shape == ref_state[k].shape and mine[k].dtype == ref_state[k].dtype, k
+    mod.load_state_dict(ref_state, strict=True)
+    assert mod.filter_size == 15 and mod.corr_size == 15

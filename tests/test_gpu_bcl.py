@@ -9,7 +9,7 @@ import torch
 import hplflownet_b200 as hpl
 from oracle import bcl as OB
 from oracle import lattice as OL
-from tests._util import assert_close, golden, golden_files, grads_from, state_from, t
+from tests._util import assert_close, assert_close_grad, golden, golden_files, grads_from, oracle_state, state_from, t
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -61,25 +61,25 @@ def test_bcl_matches_oracle(n, c_in, c_out, scale, idx_dtype):
                                 do_splat=True, do_slice=True, last_relu=False, chunk_size=-1)
     with torch.no_grad():
         mod.bias.normal_(0, 0.3)
-    state = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in mod.state_dict().items()}
+    state = oracle_state(mod)
     mod = mod.to(DEV)
     feat = torch.randn(1, c_in, n)
     gy = torch.randn(1, c_out[-1], n)
     bary, off, nbr = d["pc1_barycentric"], d["pc1_lattice_offset"], d["pc1_blur_neighbors"]
 
-    f_ref = feat.clone().requires_grad_(True)
-    y_ref = OB.bcl_forward(state, f_ref, bary, off, nbr, bary, off, do_splat=True, do_slice=True,
+    f_ref = feat.double().requires_grad_(True)          # oracle in float64 (tests/_util.py:oracle_state)
+    y_ref = OB.bcl_forward(state, f_ref, bary.double(), off, nbr, bary.double(), off, do_splat=True, do_slice=True,
                            use_norm=True, use_leaky=True, use_bias=True)
-    y_ref.backward(gy)
+    y_ref.backward(gy.double())
 
     f = feat.to(DEV).requires_grad_(True)
     bg, og, ng = bary.to(DEV), off.to(DEV).to(idx_dtype), nbr.to(DEV).to(idx_dtype)
     y = mod(f, bg, og, ng, bg, og)
     y.backward(gy.to(DEV))
     assert_close(y, y_ref.detach(), "output")
-    assert_close(f.grad, f_ref.grad, "grad_features")
+    assert_close_grad(f.grad, f_ref.grad, "grad_features")
     for k, p in mod.named_parameters():
-        assert_close(p.grad, state[k].grad, "grad " + k)
+        assert_close_grad(p.grad, state[k].grad, "grad " + k)
 
 
 def test_no_slice_no_splat_layouts():
@@ -91,22 +91,22 @@ def test_no_slice_no_splat_layouts():
     for last_relu in (False, True):
         mod = hpl.BilateralConvFlex(3, 1, 12, [20, 8], "cuda", use_bias=True, use_leaky=True, use_norm=True,
                                     do_splat=False, do_slice=False, last_relu=last_relu, chunk_size=-1)
-        state = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in mod.state_dict().items()}
+        state = oracle_state(mod)
         mod = mod.to(DEV)
         feat = torch.randn(1, 12, h)
         gy = torch.randn(1, 8, h)
-        f_ref = feat.clone().requires_grad_(True)
+        f_ref = feat.double().requires_grad_(True)
         y_ref = OB.bcl_forward(state, f_ref, None, None, nbr, None, None, do_splat=False, do_slice=False,
                                use_norm=True, use_leaky=True, use_bias=True)
-        y_ref.backward(gy)
+        y_ref.backward(gy.double())
         f = feat.to(DEV).requires_grad_(True)
         y = mod(f, None, None, nbr.to(DEV), None, None)
         y.backward(gy.to(DEV))
         assert y.shape == (1, 8, h)
         assert_close(y, y_ref.detach(), "output")
-        assert_close(f.grad, f_ref.grad, "grad_features")
+        assert_close_grad(f.grad, f_ref.grad, "grad_features")
         for k, p in mod.named_parameters():
-            assert_close(p.grad, state[k].grad, "grad " + k)
+            assert_close_grad(p.grad, state[k].grad, "grad " + k)
 
 
 def test_sparse_sum_matches_index_add():

@@ -20,6 +20,8 @@ SIGNATURES = {
     "hpl_normalize_rows": [vp, i64, i64, i64, vp, vp, vp],
     "hpl_gather_rows": [vp, i64, vp, vp, cint, vp, vp, i64, i64, vp, vp],
     "hpl_blur_gemm": [vp, i64, i64, vp, cint, i64, i64, i64, i64, vp, vp, cint, vp, i64, cint, cint, vp],
+    "hpl_blur_gemm_tc_workspace": [i64, i64, i64],
+    "hpl_blur_gemm_tc": [vp, i64, i64, vp, cint, i64, i64, i64, i64, vp, vp, cint, vp, i64, cint, vp, vp],
     "hpl_blur_wgrad": [vp, i64, i64, vp, cint, i64, i64, i64, i64, vp, i64, vp, vp, vp],
     "hpl_column_sums": [vp, i64, i64, i64, vp, vp],
     "hpl_act_backward": [vp, i64, vp, i64, i64, i64, cint, vp],
@@ -42,11 +44,11 @@ SIGNATURES = {
 }
 
 
-RETURNS_I64 = {"hpl_lattice_table_capacity", "hpl_lattice_scan_blocks"}   # sizes, not status codes
+RETURNS_I64 = {"hpl_lattice_table_capacity", "hpl_lattice_scan_blocks", "hpl_blur_gemm_tc_workspace"}   # sizes, not status codes
 
 # kernels enqueued per call (for bench.py's gpu_launches claim)
 LAUNCHES = {
-    "hpl_scatter_rows": 1, "hpl_normalize_rows": 2, "hpl_gather_rows": 1, "hpl_blur_gemm": 1,
+    "hpl_scatter_rows": 1, "hpl_normalize_rows": 2, "hpl_gather_rows": 1, "hpl_blur_gemm": 1, "hpl_blur_gemm_tc": 2,
     "hpl_blur_wgrad": 2, "hpl_act_backward": 1, "hpl_transpose_table": 1, "hpl_cm_to_rows": 1,
     "hpl_rows_to_cm": 1, "hpl_channel_sums": 1, "hpl_fill_zero": 1, "hpl_fill_i32": 1,
     "hpl_corr_gather": 1, "hpl_corr_scatter": 1, "hpl_column_sums": 1,

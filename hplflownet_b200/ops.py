@@ -10,6 +10,22 @@ from . import _lib
 
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 
+# Contraction engine: 1 = tcgen05 tensor cores with 3xTF32 compensation (default), 0 = fp32 FMA on
+# CUDA cores (parity anchor).  Both are hand-written sm_100a kernels; HPL_GEMM_PRECISION overrides.
+import os as _os
+DEFAULT_PRECISION = int(_os.environ.get("HPL_GEMM_PRECISION", "1"))
+_tc_workspace = {}
+
+
+def _workspace(device, nbytes):
+    key = (device.index, nbytes)
+    ws = _tc_workspace.get(key)
+    if ws is None:
+        ws = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+        _tc_workspace[key] = ws
+    return ws
+
+
 # bench.py sets this to a list to collect (tag, start_event, end_event) around the contraction
 # kernels (CUDA events on the launching stream); None = no instrumentation.
 PROFILE_GEMM = None
@@ -90,7 +106,7 @@ def gather_rows(rows, channels, bary, off, scale=None, bias=None):
     return y
 
 
-def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_major=False, precision=0,
+def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_major=False, precision=None,
               tag="fwd"):
     """out[v] = act(bias + sum_f x[nbr[f, v]] @ w[f]);  w (F, C, Co)."""
     _f32(x, "x"); _f32(w, "w")
@@ -106,10 +122,20 @@ def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_majo
     if out is None:
         out = (torch.empty((co, n_out_rows), dtype=torch.float32, device=x.device) if out_channel_major
                else alloc_rows(n_out_rows, co, x.device))
-    with _timed(tag):
-        _lib.call("hpl_blur_gemm", x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, f, n_out_rows, c, co,
-                  w.data_ptr(), bias.data_ptr() if bias is not None else None, act, out.data_ptr(),
-                  out.stride(0), int(out_channel_major), precision, _stream())
+    if precision is None:
+        precision = DEFAULT_PRECISION
+    bias_ptr = bias.data_ptr() if bias is not None else None
+    if precision == 1:
+        ws = _workspace(x.device, _lib.load().hpl_blur_gemm_tc_workspace(f, c, co))
+        with _timed(tag):
+            _lib.call("hpl_blur_gemm_tc", x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, f, n_out_rows, c, co,
+                      w.data_ptr(), bias_ptr, act, out.data_ptr(), out.stride(0), int(out_channel_major),
+                      ws.data_ptr(), _stream())
+    else:
+        with _timed(tag):
+            _lib.call("hpl_blur_gemm", x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, f, n_out_rows, c, co,
+                      w.data_ptr(), bias_ptr, act, out.data_ptr(), out.stride(0), int(out_channel_major), 0,
+                      _stream())
     return out
 
 

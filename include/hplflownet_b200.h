@@ -85,6 +85,16 @@ int hpl_blur_gemm(const float* in, int64_t ld_in, int64_t n_in_rows, const void*
                   const float* w, const float* bias, int act, float* out, int64_t ld_out,
                   int out_channel_major, int precision, void* stream);
 
+/* Same contract as hpl_blur_gemm on the tcgen05 tensor cores with 3xTF32 error compensation
+ * (fp32-level accuracy: every operand is split hi + lo in TF32, three MMAs per K step, fp32
+ * accumulation in tensor memory).  `workspace` holds the pre-split weight image and must be
+ * hpl_blur_gemm_tc_workspace(F, C, Co) bytes, 16-byte aligned; it is written by this call. */
+int64_t hpl_blur_gemm_tc_workspace(int64_t filter_size, int64_t c_in, int64_t c_out);
+int hpl_blur_gemm_tc(const float* in, int64_t ld_in, int64_t n_in_rows, const void* nbr, int idx64,
+                     int64_t filter_size, int64_t n_out_rows, int64_t c_in, int64_t c_out,
+                     const float* w, const float* bias, int act, float* out, int64_t ld_out,
+                     int out_channel_major, float* workspace, void* stream);
+
 /* Weight gradient of the layer above:
  *   dw[f, c, o] += sum_v in[nbr[f,v], c] * dz[v, o]        db[o] += sum_v dz[v, o]
  * dw (F, C, Co) and db (Co, may be NULL) must be zeroed by the caller; partial sums over

@@ -1,0 +1,51 @@
+"""The contraction kernels in isolation (through the ops layer / C ABI): tcgen05 3xTF32 and the
+fp32 CUDA-core anchor against a float64 torch reference of the same gather-GEMM."""
+import pytest
+import torch
+
+from hplflownet_b200 import ops
+from tests._util import assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _reference(x, nbr, w, bias, act):
+    xd = torch.cat((x.double(), torch.zeros(1, x.size(1), dtype=torch.float64, device=x.device)), 0)
+    f, c, co = w.shape
+    if nbr is None:
+        g = xd[:x.size(0), :c][None]
+    else:
+        g = xd[nbr.long()][:, :, :c]               # -1 -> the appended zero row
+    y = torch.einsum("fvc,fco->vo", g, w.double())
+    if bias is not None:
+        y = y + bias.double()
+    if act == ops.ACT_LEAKY:
+        y = torch.where(y > 0, y, 0.1 * y)
+    elif act == ops.ACT_RELU:
+        y = y.clamp_min(0)
+    return y
+
+
+@pytest.mark.parametrize("precision", [1, 0])
+@pytest.mark.parametrize("h,c,co,f,act,cm", [
+    (7599, 64, 64, 15, ops.ACT_NONE, False),     # cfg2 blur layer
+    (1000, 68, 64, 15, ops.ACT_LEAKY, False),    # bcn1: K per tap not a multiple of 16
+    (333, 20, 32, 15, ops.ACT_RELU, True),       # Co < tile, channel-major output
+    (4097, 128, 200, 1, ops.ACT_LEAKY, False),   # 1x1 layer, several N tiles, ragged Co
+    (130, 580, 72, 15, ops.ACT_NONE, True),      # bcn1_-like K = 8700
+    (5, 4, 4, 15, ops.ACT_NONE, False),          # tiny
+])
+def test_gather_gemm_matches_float64(precision, h, c, co, f, act, cm):
+    torch.manual_seed(h + c)
+    x = ops.alloc_rows(h, c, DEV, zero=True)
+    x[:, :c] = torch.randn(h, c, device=DEV)
+    w = torch.randn(f, c, co, device=DEV) * (f * c) ** -0.5
+    bias = torch.randn(co, device=DEV)
+    nbr = None
+    if f > 1:
+        nbr = torch.randint(-1, h, (f, h), device=DEV, dtype=torch.int32)
+        nbr[0] = torch.arange(h, device=DEV)
+    y = ops.blur_gemm(x, c, nbr, h, w, bias, act, out_channel_major=cm, precision=precision)
+    got = y.t()[:, :co] if cm else y[:, :co]
+    assert_close(got, _reference(x, nbr, w, bias, act), "gather-gemm precision=%d" % precision)

@@ -62,13 +62,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "{\n"
         ".reg .pred p;\n"
         "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra WAIT_DONE;\n"
         "bra WAIT_LOOP;\n"
         "WAIT_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(0x989680u)      // suspend-time hint: sleep in hardware instead of re-polling
         : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4 v) {   // shared-window store (not a generic ST)
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -159,7 +162,7 @@ gather_gemm_tc_kernel(const float* __restrict__ in, long long ld_in, long long n
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(&full_bar[s], kProducerThreads + 1);   // every producer thread + the weight loader
+            mbar_init(&full_bar[s], kProducerWarps + 1);     // one elected lane per producer warp + the weight loader
             mbar_init(&empty_bar[s], 1);                     // one tcgen05.commit
         }
         mbar_init(&accum_bar, 1);
@@ -173,6 +176,7 @@ gather_gemm_tc_kernel(const float* __restrict__ in, long long ld_in, long long n
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = tmem_base_slot;
+    const uint32_t smem_base = smem_u32(smem);
 
     if (warp < kProducerWarps) {
         // ------------------------------------------------------------------ producers
@@ -217,16 +221,18 @@ gather_gemm_tc_kernel(const float* __restrict__ in, long long ld_in, long long n
 #pragma unroll
                 for (int i = 0; i < 2; ++i) split4(pre[d][i], hi[i], lo[i]);
                 if (kb + kPrefetch < n_kb) issue(kb + kPrefetch, pre[d]);          // refill this slot
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t* a_hi = smem + stage * kStageBytes;
+                if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);     // one poller per warp
+                __syncwarp();
+                const uint32_t a_hi = smem_base + stage * kStageBytes;
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    const int off = q * (TM * 16) + (warp * 2 + i) * 128 + r8 * 16;
-                    *reinterpret_cast<float4*>(a_hi + off) = hi[i];
-                    *reinterpret_cast<float4*>(a_hi + kAHalfBytes + off) = lo[i];
+                    const uint32_t off = q * (TM * 16) + (warp * 2 + i) * 128 + r8 * 16;
+                    sts128(a_hi + off, hi[i]);
+                    sts128(a_hi + kAHalfBytes + off, lo[i]);
                 }
-                fence_proxy_async();
-                mbar_arrive(&full_bar[stage]);
+                fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_bar[stage]);   // 32 same-address arrives would serialise in the LSU
             }
         }
     } else if (warp == kProducerWarps) {
@@ -332,6 +338,227 @@ gather_gemm_tc_kernel(const float* __restrict__ in, long long ld_in, long long n
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Weight gradient on the tensor cores:   dw[(f,c), o] += sum_v in[nbr[f,v], c] * dz[v, o]
+// D (M x N) = A (M x K) . B (K x N) with M = (tap, channel) flattened, N = output channel, K = vertex.
+// Both operands are contiguous along M / N in HBM (a gathered lattice row, a dz row), i.e. "MN-major".
+// For 32-bit elements the tensor core accepts MN-major operands only in the SWIZZLE_128B_BASE32B
+// layout (probed on B200 with tools/umma_probe.cu: every other layout type yields zeros).  An atom is
+// 32 MN elements (128 B) x 4 K rows; element (m, k) of a tile lives at
+//   (m / 32) * LBO + (k / 4) * SBO + (((k % 4) * 128 + (m % 32) * 4) ^ ((k % 4) << 5))
+// i.e. the 16-byte chunk index inside a 128-byte row is XORed with 2 * (k % 4).  A quarter warp
+// stores one full 128-byte row (a permutation of its 8 chunks): conflict-free, and the matching
+// global read is 4 rows x 128 contiguous bytes per warp instruction.
+// One CTA = one 128-row M tile x one 64-column N tile x a contiguous vertex range; the partial
+// product leaves through fp32 RED.  Same 3xTF32 split and accumulator spreading as the forward.
+constexpr int WG_MAIN = 3;                                     // hi.hi accumulators per CTA
+constexpr uint32_t kMnAtom = 512;                              // 32 MN elements x 4 K rows
+constexpr uint32_t kWA_SBO = (TM / 32) * kMnAtom;              // 2048: next 4 vertices of the A tile
+constexpr uint32_t kWB_SBO = (TN / 32) * kMnAtom;              // 1024
+constexpr uint32_t kInstrDescMN = kInstrDesc | (1u << 15) | (1u << 16);   // A and B MN-major
+
+__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t addr, uint32_t sbo_bytes) {
+    return smem_desc(addr, kMnAtom, sbo_bytes) | ((uint64_t)1 << 61);    // layout type 1: SWIZZLE_128B_BASE32B
+}
+
+__device__ __forceinline__ void umma_tf32_mn(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(kInstrDescMN), "r"(accumulate)
+        : "memory");
+}
+
+template <bool I64>
+__global__ void __launch_bounds__(kThreads, 2)
+wgrad_tc_kernel(const float* __restrict__ in, long long ld_in, long long n_in_rows, const void* __restrict__ nbr,
+                int filter_size, long long n_out_rows, int c_in, int c_out, const float* __restrict__ dz, long long ld_dz,
+                float* __restrict__ dw, long long rows_per_split) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], accum_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * TM, o0 = blockIdx.z * TN;
+    const int m_total = filter_size * c_in;
+    const long long v_lo = rows_per_split * blockIdx.x;
+    const long long v_hi = min(n_out_rows, v_lo + rows_per_split);
+    const int n_kb = v_lo < v_hi ? (int)((v_hi - v_lo + TK - 1) / TK) : 0;
+    const uint32_t tmem_cols = (uint32_t)(TN * (WG_MAIN + 1));
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], kProducerWarps);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kProducerWarps) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_slot;
+    const uint32_t smem_base = smem_u32(smem);
+
+    if (warp < kProducerWarps) {
+        // -------------------------------------------------------------- producers (A gathered, B = dz)
+        const int kq = lane >> 3, c8 = lane & 7;       // K row inside the group of 4, 16-byte chunk of the 128-byte row
+        const uint32_t swz = kq * 128 + ((c8 ^ (2 * kq)) * 16);
+        // two A chunks per thread: (K group, MN atom) = warp task; tap / channel fixed for the whole kernel
+        int tap[2], ch[2], kk_a[2];
+        uint32_t off_a[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int wt = warp * 2 + i;
+            const int kgrp = wt & 3, atom = wt >> 2;
+            kk_a[i] = kgrp * 4 + kq;
+            const int m = m0 + atom * 32 + c8 * 4;
+            tap[i] = m < m_total ? m / c_in : -1;
+            ch[i] = m < m_total ? m - tap[i] * c_in : 0;
+            off_a[i] = kgrp * kWA_SBO + atom * kMnAtom + swz;
+        }
+        // one B chunk per thread
+        const int kgrp_b = warp & 3, atom_b = warp >> 2;
+        const int kk_b = kgrp_b * 4 + kq, n_b = atom_b * 32 + c8 * 4;
+        const uint32_t off_b = kgrp_b * kWB_SBO + atom_b * kMnAtom + swz;
+        const bool b_live = o0 + n_b < c_out;
+
+        float4 pre[kPrefetch][3];
+        auto issue = [&](int kb, float4* dst) {
+            const long long vb = v_lo + (long long)kb * TK;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const long long v = vb + kk_a[i];
+                int r = -1;
+                if (v < v_hi && tap[i] >= 0) {
+                    r = nbr != nullptr ? load_idx<I64>(nbr, (long long)tap[i] * n_out_rows + v) : (int)v;
+                    if (r >= n_in_rows) r = -1;
+                }
+                dst[i] = r >= 0 ? __ldg(reinterpret_cast<const float4*>(in + (long long)r * ld_in + ch[i]))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            const long long v = vb + kk_b;
+            dst[2] = (v < v_hi && b_live) ? __ldg(reinterpret_cast<const float4*>(dz + v * ld_dz + o0 + n_b))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+#pragma unroll
+        for (int d = 0; d < kPrefetch; ++d)
+            if (d < n_kb) issue(d, pre[d]);
+
+        for (int kb0 = 0; kb0 < n_kb; kb0 += kPrefetch) {
+#pragma unroll
+            for (int d = 0; d < kPrefetch; ++d) {
+                const int kb = kb0 + d;
+                if (kb >= n_kb) break;
+                const int stage = kb % kStages;
+                const uint32_t phase = (kb / kStages) & 1;
+                float4 hi[3], lo[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) split4(pre[d][i], hi[i], lo[i]);
+                if (kb + kPrefetch < n_kb) issue(kb + kPrefetch, pre[d]);
+                if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
+                __syncwarp();
+                const uint32_t a_hi = smem_base + stage * kStageBytes;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    sts128(a_hi + off_a[i], hi[i]);
+                    sts128(a_hi + kAHalfBytes + off_a[i], lo[i]);
+                }
+                sts128(a_hi + 2 * kAHalfBytes + off_b, hi[2]);
+                sts128(a_hi + 2 * kAHalfBytes + kBHalfBytes + off_b, lo[2]);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_bar[stage]);
+            }
+        }
+    } else if (warp == kProducerWarps) {
+        // -------------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            int last_g = -1;
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int stage = kb % kStages;
+                const int g = (int)((long long)kb * WG_MAIN / n_kb);
+                const uint32_t tmem_main = tmem_d + (uint32_t)(TN * (1 + g));
+                mbar_wait(&full_bar[stage], (kb / kStages) & 1);
+                tc_fence_after();
+                const uint32_t a_hi = smem_base + stage * kStageBytes;
+                const uint32_t a_lo = a_hi + kAHalfBytes;
+                const uint32_t b_hi = a_hi + 2 * kAHalfBytes;
+                const uint32_t b_lo = b_hi + kBHalfBytes;
+#pragma unroll
+                for (int j = 0; j < TK / 8; ++j) {
+                    const uint64_t dah = smem_desc_mn(a_hi + j * 2 * kWA_SBO, kWA_SBO);
+                    const uint64_t dal = smem_desc_mn(a_lo + j * 2 * kWA_SBO, kWA_SBO);
+                    const uint64_t dbh = smem_desc_mn(b_hi + j * 2 * kWB_SBO, kWB_SBO);
+                    const uint64_t dbl = smem_desc_mn(b_lo + j * 2 * kWB_SBO, kWB_SBO);
+                    umma_tf32_mn(tmem_d, dal, dbh, (kb | j) != 0);
+                    umma_tf32_mn(tmem_d, dah, dbl, 1);
+                    umma_tf32_mn(tmem_main, dah, dbh, g == last_g);
+                    last_g = g;
+                }
+                umma_commit(&empty_bar[stage]);
+            }
+            umma_commit(&accum_bar);
+        }
+    }
+
+    // ------------------------------------------------------------------ epilogue (warps 0-3): RED into dw
+    if (warp < 4 && n_kb > 0) {
+        mbar_wait(&accum_bar, 0);
+        tc_fence_after();
+        const int m = m0 + warp * 32 + lane;
+        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int cb = 0; cb < TN; cb += 16) {
+            float sum[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sum[j] = 0.f;
+            for (int g = 0; g <= WG_MAIN; ++g) {
+                if (g > 0) {
+                    // accumulator g-1 was written iff some kb maps to it: kb*WG_MAIN/n_kb == g-1
+                    const int first_kb = ((g - 1) * n_kb + WG_MAIN - 1) / WG_MAIN;
+                    if (first_kb >= n_kb || (int)((long long)first_kb * WG_MAIN / n_kb) != g - 1) continue;
+                }
+                uint32_t v[16];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr + g * TN + cb));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sum[j] += __uint_as_float(v[j]);
+            }
+            if (m < m_total) {
+                float* p = dw + (long long)m * c_out + o0 + cb;
+                if (o0 + cb + 15 < c_out && (c_out & 3) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) red_add_f32x4(p + j, make_float4(sum[j], sum[j + 1], sum[j + 2], sum[j + 3]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (o0 + cb + j < c_out) atomicAdd(p + j, sum[j]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kProducerWarps) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -373,6 +600,45 @@ int hpl_blur_gemm_tc(const float* in, int64_t ld_in, int64_t n_in_rows, const vo
         gather_gemm_tc_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, (int)c_in,
                                                                          (int)c_out, kb_per_tap, workspace, bias, act, out, ld_out,
                                                                          out_channel_major, n_main);
+    HPL_RETURN_LAST();
+}
+
+int hpl_blur_wgrad_tc(const float* in, int64_t ld_in, int64_t n_in_rows, const void* nbr, int idx64, int64_t filter_size,
+                      int64_t n_out_rows, int64_t c_in, int64_t c_out, const float* dz, int64_t ld_dz, float* dw, float* db,
+                      void* stream) {
+    HPL_CHECK_ARG(in && dz && dw && c_in > 0 && c_out > 0 && filter_size > 0 && c_in % 4 == 0);
+    HPL_CHECK_ARG(ld_in % 4 == 0 && ld_in >= c_in && ((uintptr_t)in & 15) == 0);
+    HPL_CHECK_ARG(ld_dz % 4 == 0 && ld_dz >= c_out && ((uintptr_t)dz & 15) == 0 && ((uintptr_t)dw & 15) == 0);
+    HPL_CHECK_ARG(nbr != nullptr || filter_size == 1);
+    if (n_out_rows == 0) return 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        attr_set = true;
+    }
+    const long long m_tiles = (filter_size * c_in + TM - 1) / TM, n_tiles = (c_out + TN - 1) / TN;
+    const long long base = m_tiles * n_tiles;
+    long long splits = (4LL * num_sms() + base - 1) / base;                 // ~2 waves at 2 CTAs / SM
+    const long long max_splits = (n_out_rows + 8 * TK - 1) / (8 * TK);      // at least 8 stages per CTA
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    long long rows_per_split = (n_out_rows + splits - 1) / splits;
+    rows_per_split = (rows_per_split + TK - 1) / TK * TK;
+    // keep the accumulate steps per hi.hi accumulator <= ~160 (see the forward kernel)
+    const long long max_rows = 160LL * WG_MAIN * 8;
+    if (rows_per_split > max_rows) rows_per_split = max_rows;
+    splits = (n_out_rows + rows_per_split - 1) / rows_per_split;
+    HPL_CHECK_ARG(m_tiles <= 65535 && n_tiles <= 65535);
+    dim3 grid((unsigned)splits, (unsigned)m_tiles, (unsigned)n_tiles);
+    cudaStream_t s = as_stream(stream);
+    if (idx64)
+        wgrad_tc_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, (int)c_in,
+                                                                  (int)c_out, dz, ld_dz, dw, rows_per_split);
+    else
+        wgrad_tc_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, (int)c_in,
+                                                                   (int)c_out, dz, ld_dz, dw, rows_per_split);
+    if (db != nullptr) return hpl_column_sums(dz, ld_dz, n_out_rows, c_out, db, stream);
     HPL_RETURN_LAST();
 }
 

@@ -139,7 +139,7 @@ def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_majo
     return out
 
 
-def blur_wgrad(x, c_in, nbr, n_out_rows, dz, c_out, filter_size, want_db=True):
+def blur_wgrad(x, c_in, nbr, n_out_rows, dz, c_out, filter_size, want_db=True, precision=None):
     """Returns dw (F, C, Co), db (Co)."""
     _f32(x, "x"); _f32(dz, "dz")
     if nbr is not None:
@@ -149,8 +149,11 @@ def blur_wgrad(x, c_in, nbr, n_out_rows, dz, c_out, filter_size, want_db=True):
         nbr_ptr, i64 = None, 0
     dw = torch.zeros((filter_size, c_in, c_out), dtype=torch.float32, device=x.device)
     db = torch.zeros(c_out, dtype=torch.float32, device=x.device) if want_db else None
+    if precision is None:
+        precision = DEFAULT_PRECISION
+    fn = "hpl_blur_wgrad_tc" if (precision == 1 and c_in % 4 == 0) else "hpl_blur_wgrad"
     with _timed("wgrad"):
-        _lib.call("hpl_blur_wgrad", x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, filter_size, n_out_rows,
+        _lib.call(fn, x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, filter_size, n_out_rows,
                   c_in, c_out, dz.data_ptr(), dz.stride(0), dw.data_ptr(), db.data_ptr() if want_db else None,
                   _stream())
     return dw, db

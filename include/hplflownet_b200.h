@@ -103,6 +103,12 @@ int hpl_blur_wgrad(const float* in, int64_t ld_in, int64_t n_in_rows, const void
                    int64_t filter_size, int64_t n_out_rows, int64_t c_in, int64_t c_out,
                    const float* dz, int64_t ld_dz, float* dw, float* db, void* stream);
 
+/* Same contract as hpl_blur_wgrad on the tcgen05 tensor cores (3xTF32, see hpl_blur_gemm_tc).
+ * Requires c_in % 4 == 0. */
+int hpl_blur_wgrad_tc(const float* in, int64_t ld_in, int64_t n_in_rows, const void* nbr, int idx64,
+                      int64_t filter_size, int64_t n_out_rows, int64_t c_in, int64_t c_out,
+                      const float* dz, int64_t ld_dz, float* dw, float* db, void* stream);
+
 /* sums[c] += sum_v rows[v, c]  (conv bias gradients). rows (n_rows, ld) vertex-major. */
 int hpl_column_sums(const float* rows, int64_t ld, int64_t n_rows, int64_t channels, float* sums,
                     void* stream);

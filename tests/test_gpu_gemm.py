@@ -49,3 +49,30 @@ def test_gather_gemm_matches_float64(precision, h, c, co, f, act, cm):
     y = ops.blur_gemm(x, c, nbr, h, w, bias, act, out_channel_major=cm, precision=precision)
     got = y.t()[:, :co] if cm else y[:, :co]
     assert_close(got, _reference(x, nbr, w, bias, act), "gather-gemm precision=%d" % precision)
+
+
+@pytest.mark.parametrize("precision", [1, 0])
+@pytest.mark.parametrize("h,c,co,f", [
+    (7599, 64, 64, 15),       # cfg2
+    (242429 // 4, 64, 64, 15),  # a batch of clouds: many vertex ranges per CTA column
+    (1000, 68, 64, 15),       # M tiles straddle taps
+    (333, 20, 32, 15),
+    (4097, 128, 200, 1),      # 1x1 layer, ragged Co
+    (130, 580, 72, 15),       # K = 8700 forward, M = 8700 here
+    (5, 4, 4, 15),
+])
+def test_wgrad_matches_float64(precision, h, c, co, f):
+    torch.manual_seed(h + co)
+    x = ops.alloc_rows(h, c, DEV, zero=True)
+    x[:, :c] = torch.randn(h, c, device=DEV)
+    dz = ops.alloc_rows(h, co, DEV, zero=True)
+    dz[:, :co] = torch.randn(h, co, device=DEV)
+    nbr = None
+    if f > 1:
+        nbr = torch.randint(-1, h, (f, h), device=DEV, dtype=torch.int64)
+    dw, db = ops.blur_wgrad(x, c, nbr, h, dz, co, f, precision=precision)
+    xd = torch.cat((x.double(), torch.zeros(1, x.size(1), dtype=torch.float64, device=DEV)), 0)
+    g = xd[:h, :c][None] if nbr is None else xd[nbr][:, :, :c]
+    want = torch.einsum("fvc,vo->fco", g, dz[:, :co].double())
+    assert_close(dw, want, "wgrad precision=%d" % precision)
+    assert_close(db, dz[:, :co].double().sum(0), "bias grad")

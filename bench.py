@@ -28,6 +28,9 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 METRIC = "point-clouds/sec (BCL fwd+bwd, 8192 pts, d=3, 64ch)"
+# dram__bytes_read.sum + dram__bytes_write.sum of one gather_gemm_tc_kernel launch on this workload
+# (ncu --set full, profiles/r01_tc_gemm_metrics.md); algorithmic bytes are ~139 MB.
+NCU_TRAFFIC_BYTES = 121.0e6
 N_POINTS, CHANNELS, SCALE = 8192, 64, 1.0
 
 
@@ -293,24 +296,34 @@ def run_ours(args):
     value = world * B * args.steps / (ms * 1e-3)
     e2e_value = world * B * e2e_steps / e2e_s
 
-    # ---- roofline of the dominant kernel (the blur gather-GEMM forward launch)
+    # ---- roofline of the dominant kernel: the blur gather-GEMM (forward launch), tcgen05 3xTF32.
+    # achieved = algorithmic FLOPs (2*F*C*Co per vertex) / CUDA-event duration on the launch
+    # stream; peak = measured dense bf16 tensor throughput (MEASURED_PEAKS.json, burst).  A 3xTF32
+    # contraction issues 3 TF32 MMAs (half the bf16 rate) per algorithmic MAC, so its ceiling is peak/6.
     peaks = measured_peaks()
-    fwd_gemm = [a.elapsed_time(b) for tag, a, b in gemm_events if tag == "fwd"]
-    gemm_ms = sum(fwd_gemm) / max(1, len(fwd_gemm))
-    gemm_bytes = blur_fwd_bytes(h_tot, CHANNELS, CHANNELS)
+    by_tag = {}
+    for tag, a, b in gemm_events:
+        by_tag.setdefault(tag, []).append(a.elapsed_time(b))
+    avg = {k: sum(v) / len(v) for k, v in by_tag.items()}
+    gemm_ms = avg.get("fwd", float("nan"))
     gemm_flops = 2.0 * 15 * CHANNELS * CHANNELS * h_tot
-    achieved = gemm_bytes / (gemm_ms * 1e-3) / 1e9
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
     fb, bb = algorithmic_bytes(n_tot, h_tot, CHANNELS, CHANNELS)
     all_gemm_ms = sum(a.elapsed_time(b) for _, a, b in gemm_events) / args.steps
+    engine = "tcgen05 3xTF32" if ops.DEFAULT_PRECISION == 1 else "fp32 CUDA-core FMA"
     roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-        "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
-        "kernel": "gather_gemm_kernel (blur forward, fp32 CUDA-core FMA)",
-        "kernel_ms": gemm_ms, "kernel_tflops_fp32": gemm_flops / (gemm_ms * 1e-3) / 1e12,
-        "kernel_share_of_step": all_gemm_ms / (ms / args.steps),
-        "note": "compute-bound fp32 contraction (AI ~205 FLOP/B): the HBM fraction is low by construction; "
-                "kernel_tflops_fp32 vs ~74.5 TFLOP/s CUDA-core peak is the relevant ratio this round",
+        "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+        "frac": achieved / peaks["bf16_tflops"], "traffic": NCU_TRAFFIC_BYTES, "peak_source": peaks["source"],
+        "kernel": "gather_gemm_tc_kernel (blur forward, %s)" % engine,
+        "kernel_ms": gemm_ms, "kernel_ms_by_role": avg,
+        "frac_of_3xtf32_ceiling": achieved / (peaks["bf16_tflops"] / 6.0),
+        "kernel_algorithmic_bytes": blur_fwd_bytes(h_tot, CHANNELS, CHANNELS),
+        "kernel_algorithmic_gbs": blur_fwd_bytes(h_tot, CHANNELS, CHANNELS) / (gemm_ms * 1e-3) / 1e9,
+        "contraction_share_of_step": all_gemm_ms / (ms / args.steps),
         "whole_step_algorithmic_gbs": (fb + bb) / (ms / args.steps * 1e-3) / 1e9,
+        "whole_step_frac_of_hbm_peak": (fb + bb) / (ms / args.steps * 1e-3) / 1e9 / peaks["hbm_gbs"],
+        "note": "dense fp32-accurate contraction (AI ~205 FLOP/B) -> tensor-bound, not HBM-bound; ncu: tensor pipe "
+                "~20% active, L1/shared data pipe ~80% (operand staging of a gathered A) -- see profiles/",
     }
 
     cpu = cpu_baseline_leg()

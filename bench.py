@@ -207,7 +207,8 @@ def run_ours(args):
 
     # ---- synthetic batch: B distinct clouds for this rank (weak scaling: B per GPU)
     mod = make_state().to(dev)
-    items = [cloud_tables(rank * B + s) for s in range(B)]
+    from hplflownet_b200 import sharding
+    items = [cloud_tables(s) for s in sharding.cloud_ids(rank, world, B)]
     batch = concat_lattices(items)
     n_tot, h_tot = sum(batch["point_counts"]), sum(batch["vertex_counts"])
     torch.manual_seed(1000 + rank)
@@ -284,17 +285,14 @@ def run_ours(args):
     d2h = 4 + sum(p.numel() * 4 for p in params)
 
     # ---- max over ranks
-    if world > 1:
-        tt = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, e2e_s = tt.tolist()
+    ms, e2e_s = sharding.max_over_ranks([ms, e2e_s], device=dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    value = world * B * args.steps / (ms * 1e-3)
-    e2e_value = world * B * e2e_steps / e2e_s
+    value = sharding.job_throughput(B * args.steps, world, ms * 1e-3)
+    e2e_value = sharding.job_throughput(B * e2e_steps, world, e2e_s)
 
     # ---- roofline of the dominant kernel: the blur gather-GEMM (forward launch), tcgen05 3xTF32.
     # achieved = algorithmic FLOPs (2*F*C*Co per vertex) / CUDA-event duration on the launch

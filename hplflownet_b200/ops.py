@@ -18,7 +18,8 @@ _tc_workspace = {}
 
 
 def _workspace(device, nbytes):
-    key = (device.index, nbytes)
+    # rewritten by every call that uses it, so it is private to one (device, stream)
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, nbytes)
     ws = _tc_workspace.get(key)
     if ws is None:
         ws = torch.empty(nbytes // 4, dtype=torch.float32, device=device)

@@ -55,7 +55,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -326,6 +326,7 @@ def run_ours(args):
 
     cpu = cpu_baseline_leg()
     lattice = lattice_leg(dev)
+    model_fwd = model_leg(dev)
 
     line = {
         "metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": world, "steps": args.steps,
@@ -340,11 +341,55 @@ def run_ours(args):
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "clouds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps},
-        "gpu_launches": launches, "clocks": clocks, "lattice_build": lattice,
+        "gpu_launches": launches, "clocks": clocks, "lattice_build": lattice, "model_forward": model_fwd,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def model_leg(dev):
+    """Secondary number (BASELINE configs[3]): full HPLFlowNet forward, random weights, one synthetic
+    FlyingThings3D-shaped 8192-point pair, evaluate mode; with and without the GPU lattice build."""
+    import torch
+    from hplflownet_b200.HPLFlowNet import HPLFlowNet
+    from hplflownet_b200.synthetic import frustum_pair
+    from hplflownet_b200.transforms import GenerateDataUnsymmetric, collate_batch1
+
+    class A:
+        dim = 3
+        evaluate = True
+        use_leaky = bcn_use_bias = bcn_use_norm = True
+        last_relu = False
+        DEVICE = "cuda"
+        scales_filter_map = [[3., 1, -1, -1], [2., 1, -1, -1], [1., 1, 1, 1], [.5, 1, 1, 1], [.25, 1, 1, 1],
+                             [.125, 1, 1, 1], [.0625, 1, 1, 1]]
+    torch.manual_seed(0)
+    model = HPLFlowNet(A()).to(dev).eval()
+    gen = GenerateDataUnsymmetric(A(), device=dev, index_dtype=torch.int32)
+    pc1, pc2 = frustum_pair(N_POINTS, 7)
+    a, b = torch.from_numpy(pc1.T.copy()).to(dev), torch.from_numpy(pc2.T.copy()).to(dev)
+
+    def run(build):
+        with torch.no_grad():
+            gd = collate_batch1(gen.build(a, b)) if build else run.gd
+            return model(a[None], b[None], gd)
+    run.gd = collate_batch1(gen.build(a, b))
+    out = {}
+    for name, build in (("forward_ms", False), ("build_plus_forward_ms", True)):
+        for _ in range(3):
+            run(build)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 8
+        for _ in range(reps):
+            y = run(build)
+        torch.cuda.synchronize()
+        out[name] = 1e3 * (time.perf_counter() - t0) / reps
+    out.update({"workload": "HPLFlowNet forward, 8192+8192-pt pair, 7 scales, evaluate mode, random weights",
+                "pairs_per_s": 1e3 / out["build_plus_forward_ms"], "output_finite": bool(torch.isfinite(y).all()),
+                "note": "reference CPU forward: 13.8 s/pair + 4.1-4.9 s lattice build (SURVEY §6, 8 vCPU)"})
+    return out
 
 
 def lattice_leg(dev):
@@ -422,7 +467,7 @@ def cpu_baseline_leg():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clouds", type=int, default=32, help="distinct clouds per GPU per step")

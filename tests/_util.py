@@ -100,3 +100,33 @@ def assert_close_grad(got, ref, what=""):
         return
     e_l2 = ((g - r).norm() / r.norm().clamp_min(1e-30)).item()
     assert e_max <= 3e-2 and e_l2 <= 3e-3, "%s: rel err max %.3e, L2 %.3e" % (what, e_max, e_l2)
+
+
+def name_keyed_init_(module, seed=0):
+    """Deterministic parameter values that depend only on (parameter name, shape, seed) -- not on module
+    construction order or the RNG stream -- so the reference model (oracle/make_golden.py) and the B200
+    model get identical weights without shipping 77 MB of state_dict.  N(0, 1/fan_in) weights, small biases."""
+    import zlib
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            g = torch.Generator().manual_seed((zlib.crc32(name.encode()) + 7919 * seed) % (2 ** 31))
+            if p.dim() > 1:
+                fan_in = p[0].numel()
+                p.copy_(torch.randn(p.shape, generator=g) * fan_in ** -0.5)
+            else:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+    return module
+
+
+class ModelArgs:
+    """The attributes HPLFlowNet reads from its args object (models/HPLFlowNet.py:12-35), with the values of
+    configs/test_ours_FlyingThings3D.yaml."""
+    dim = 3
+    evaluate = True
+    use_leaky = True
+    bcn_use_bias = True
+    bcn_use_norm = True
+    last_relu = False
+    DEVICE = "cuda"
+    scales_filter_map = [[3., 1, -1, -1], [2., 1, -1, -1], [1., 1, 1, 1], [.5, 1, 1, 1], [.25, 1, 1, 1],
+                         [.125, 1, 1, 1], [.0625, 1, 1, 1]]

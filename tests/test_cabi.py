@@ -90,3 +90,17 @@ def test_corr_state_dict_layout_matches_reference(name):
         assert mine[k].shape == ref_state[k].shape and mine[k].dtype == ref_state[k].dtype, k
     mod.load_state_dict(ref_state, strict=True)
     assert mod.filter_size == 15 and mod.corr_size == 15
+
+
+def test_model_state_dict_is_reference_layout():
+    from hplflownet_b200.HPLFlowNet import HPLFlowNet
+    from tests._util import ModelArgs
+    model = HPLFlowNet(ModelArgs())
+    sd = model.state_dict()
+    assert sum(p.numel() for p in model.parameters()) == 19303843
+    for k in ("conv1.0.composed_module.0.weight", "bcn1.blur_conv.0.composed_module.0.weight", "bcn1.blur_conv.1.bias",
+              "bcn1_.bias", "bcn1_.out_indices", "corr1.corr_conv.0.composed_module.0.weight", "corr2.feat1_indices",
+              "conv4.weight"):
+        assert k in sd, k
+    assert sd["bcn1_.blur_conv.0.composed_module.0.weight"].shape == (1024, 580, 15, 1)
+    assert sd["corr2.corr_conv.0.composed_module.0.weight"].shape == (32, 192, 1, 15, 1)

@@ -104,3 +104,20 @@ def test_corr_oracle_matches_reference(name):
         assert_close(prev.grad, g["grad_prev"], "grad_prev")
     for k, ref in grads_from(g).items():
         assert_close(state[k].grad, ref, "grad " + k)
+
+
+def test_model_oracle_matches_reference_output():
+    # full HPLFlowNet forward: oracle composition vs the reference model's own output
+    from oracle import hplflownet as OM
+    from hplflownet_b200.HPLFlowNet import HPLFlowNet
+    from tests._util import ModelArgs, name_keyed_init_
+    g = golden("model_frustum256.npz")
+    model = name_keyed_init_(HPLFlowNet(ModelArgs()), int(g["seed"]))
+    state = {k: v.detach() for k, v in model.state_dict().items()}
+    gd = OL.generate(g["pc1"], g["pc2"], ModelArgs.scales_filter_map)
+    gd = [{k: (torch.from_numpy(v)[None] if not isinstance(v, int) else v) for k, v in d.items()} for d in gd]
+    pc1, pc2 = [torch.from_numpy(np.ascontiguousarray(g[k].T))[None] for k in ("pc1", "pc2")]
+    with torch.no_grad():
+        out = OM.forward(state, pc1, pc2, gd)
+    assert out.shape == (1, 3, 256)
+    assert_close(out, g["output"], "flow", tol=1e-5)

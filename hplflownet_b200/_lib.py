@@ -21,9 +21,9 @@ SIGNATURES = {
     "hpl_gather_rows": [vp, i64, vp, vp, cint, vp, vp, i64, i64, vp, vp],
     "hpl_blur_gemm": [vp, i64, i64, vp, cint, i64, i64, i64, i64, vp, vp, cint, vp, i64, cint, cint, vp],
     "hpl_blur_gemm_tc_workspace": [i64, i64, i64],
-    "hpl_blur_gemm_tc": [vp, i64, i64, vp, cint, i64, i64, i64, i64, vp, vp, cint, vp, i64, cint, vp, vp],
+    "hpl_blur_gemm_tc": [vp, i64, i64, vp, cint, i64, i64, i64, i64, vp, vp, cint, vp, i64, cint, vp, vp, vp],
     "hpl_blur_wgrad": [vp, i64, i64, vp, cint, i64, i64, i64, i64, vp, i64, vp, vp, vp],
-    "hpl_blur_wgrad_tc": [vp, i64, i64, vp, cint, i64, i64, i64, i64, vp, i64, vp, vp, vp],
+    "hpl_blur_wgrad_tc": [vp, i64, i64, vp, cint, i64, i64, i64, i64, vp, i64, vp, vp, vp, vp],
     "hpl_column_sums": [vp, i64, i64, i64, vp, vp],
     "hpl_act_backward": [vp, i64, vp, i64, i64, i64, cint, vp],
     "hpl_transpose_table": [vp, cint, i64, i64, vp, i64, vp, vp],

@@ -7,7 +7,7 @@ BilateralCorrelationFlex (corr_conv / blur_conv, models/bnn_flow.py:59-91).  Eac
 from . import ops
 
 
-def forward(x, c_in, n_rows, layers, first_nbr=None, last_channel_major=False):
+def forward(x, c_in, n_rows, layers, first_nbr=None, last_channel_major=False, first_row_scale=None):
     """Returns (xs, chans, out_cm): xs[l] is the vertex-major input of layer l and xs[-1] the final
     vertex-major output -- unless the last layer is written channel-major directly (only when it has
     no activation), in which case it is returned as out_cm and not kept in xs."""
@@ -16,7 +16,7 @@ def forward(x, c_in, n_rows, layers, first_nbr=None, last_channel_major=False):
         last = l == len(layers) - 1
         direct_cm = last and last_channel_major and act == ops.ACT_NONE
         y = ops.blur_gemm(xs[-1], chans[-1], first_nbr if l == 0 else None, n_rows, w, b,
-                          act, out_channel_major=direct_cm)
+                          act, out_channel_major=direct_cm, row_scale=first_row_scale if l == 0 else None)
         if direct_cm:
             out_cm = y
         else:
@@ -25,7 +25,8 @@ def forward(x, c_in, n_rows, layers, first_nbr=None, last_channel_major=False):
     return xs, chans, out_cm
 
 
-def backward(dx, xs, chans, layers, n_rows, first_nbr, first_nbr_t, need_input_grad, need_param_grad):
+def backward(dx, xs, chans, layers, n_rows, first_nbr, first_nbr_t, need_input_grad, need_param_grad,
+             first_row_scale=None):
     """dx: gradient w.r.t. the stack's (post-activation) output, vertex-major, modified in place.
     first_nbr_t: callable returning the transposed table of the first layer (built lazily).
     Returns (dx_in or None, [(dw (F, C, Co), db (Co)) or None per layer])."""
@@ -36,7 +37,8 @@ def backward(dx, xs, chans, layers, n_rows, first_nbr, first_nbr_t, need_input_g
             ops.act_backward_(dx, xs[l + 1], chans[l + 1], act)
         tbl = first_nbr if l == 0 else None
         if need_param_grad[l]:
-            grads[l] = ops.blur_wgrad(xs[l], chans[l], tbl, n_rows, dx, chans[l + 1], w.size(0), want_db=b is not None)
+            grads[l] = ops.blur_wgrad(xs[l], chans[l], tbl, n_rows, dx, chans[l + 1], w.size(0), want_db=b is not None,
+                                      row_scale=first_row_scale if l == 0 else None)
         if l > 0 or need_input_grad:
             wd = w.transpose(1, 2).contiguous()                       # (F, Co, C)
             tbl_t = first_nbr_t() if (l == 0 and first_nbr is not None) else None

@@ -21,6 +21,8 @@ from .module_utils import Conv2dReLU
 
 __all__ = ["BilateralConvFlex", "SparseSum", "sparse_sum"]
 
+FUSE_NORMALISATION = False
+
 
 def _act_code(has_act, use_leaky):
     if not has_act:
@@ -85,18 +87,24 @@ class _BCLFunction(torch.autograd.Function):
         c_in = feat.size(0)
         nbr2 = nbr[0].contiguous()                           # (F, H)
         h = nbr2.size(1)
-        inv = None
+        inv, fuse_norm = None, False
         if do_splat:
             bary_i, off_i = in_bary[0].contiguous(), in_off[0].contiguous()
             lat, wsum = ops.scatter_rows(feat, bary_i, off_i, h, use_norm)
             if use_norm:
-                inv = ops.normalize_rows_(lat, c_in, wsum)
+                # The contraction kernels can also apply 1/(wsum+1e-5) while gathering (row_scale), saving
+                # this pass; measured on B200 the extra dependent load costs the forward GEMM more (+70 us
+                # per 32 clouds) than the 25 us pass it removes, so it is off by default.
+                fuse_norm = FUSE_NORMALISATION and ops.tc_path(c_in)
+                inv = ops.reciprocal_(wsum) if fuse_norm else ops.normalize_rows_(lat, c_in, wsum)
         else:
             bary_i = off_i = None
             lat = ops.cm_to_rows(feat)
 
         layers = [(kernel_weight(params[2 * l]), params[2 * l + 1].detach(), acts[l]) for l in range(len(acts))]
-        xs, chans, out_cm = _stack.forward(lat, c_in, h, layers, nbr2, last_channel_major=not do_slice)
+        scale0 = inv if (do_splat and use_norm and fuse_norm) else None
+        xs, chans, out_cm = _stack.forward(lat, c_in, h, layers, nbr2, last_channel_major=not do_slice,
+                                           first_row_scale=scale0)
 
         if do_slice:
             bary_o, off_o = out_bary[0].contiguous(), out_off[0].contiguous()
@@ -107,7 +115,7 @@ class _BCLFunction(torch.autograd.Function):
             out = out_cm if out_cm is not None else ops.rows_to_cm(xs[-1], chans[-1])
 
         ctx.cfg, ctx.chans, ctx.h = cfg, chans, h
-        ctx.xs, ctx.layers, ctx.inv = xs, layers, inv
+        ctx.xs, ctx.layers, ctx.inv, ctx.scale0 = xs, layers, inv, scale0
         ctx.idx = (bary_i, off_i, nbr2, bary_o, off_o)
         ctx.has_slice_bias = slice_bias is not None
         ctx.param_shapes = [p.shape for p in params]
@@ -130,7 +138,7 @@ class _BCLFunction(torch.autograd.Function):
         need_feat = ctx.needs_input_grad[1]
         need_param = [ctx.needs_input_grad[8 + 2 * l] or ctx.needs_input_grad[9 + 2 * l] for l in range(len(layers))]
         dx, pg = _stack.backward(dx, xs, chans, layers, h, nbr2, lambda: ops.transpose_table(nbr2, h),
-                                 need_feat, need_param)
+                                 need_feat, need_param, first_row_scale=ctx.scale0)
         grads = []
         for l, g_l in enumerate(pg):
             if g_l is None:

@@ -248,15 +248,26 @@ wgrad_kernel(const float* __restrict__ in, long long ld_in, long long n_in_rows,
     }
 }
 
-// db[o] += sum_v dz[v, o]
-__global__ void column_sums_kernel(const float* __restrict__ dz, long long ld_dz, long long n_rows, int c_out,
-                                   float* __restrict__ db, long long rows_per_block) {
-    const int o = blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= c_out) return;
+// db[o] += sum_v dz[v, o].  Block = 64 columns x 4 row lanes; each block reduces a slab of rows.
+__global__ void __launch_bounds__(256)
+column_sums_kernel(const float* __restrict__ dz, long long ld_dz, long long n_rows, int c_out,
+                   float* __restrict__ db, long long rows_per_block) {
+    __shared__ float part[4][64];
+    const int col = threadIdx.x & 63, lane_r = threadIdx.x >> 6;
+    const int o = blockIdx.x * 64 + col;
     const long long lo = rows_per_block * blockIdx.y, hi = min(n_rows, lo + rows_per_block);
-    float acc = 0.f;
-    for (long long v = lo; v < hi; ++v) acc += __ldg(dz + v * ld_dz + o);
-    if (lo < hi) atomicAdd(db + o, acc);
+    float acc0 = 0.f, acc1 = 0.f;
+    if (o < c_out) {
+        long long v = lo + lane_r;
+        for (; v + 4 < hi; v += 8) {
+            acc0 += __ldg(dz + v * ld_dz + o);
+            acc1 += __ldg(dz + (v + 4) * ld_dz + o);
+        }
+        if (v < hi) acc0 += __ldg(dz + v * ld_dz + o);
+    }
+    part[lane_r][col] = acc0 + acc1;
+    __syncthreads();
+    if (lane_r == 0 && o < c_out && lo < hi) atomicAdd(db + o, (part[0][col] + part[1][col]) + (part[2][col] + part[3][col]));
 }
 
 }  // namespace
@@ -288,11 +299,11 @@ int hpl_blur_gemm(const float* in, int64_t ld_in, int64_t n_in_rows, const void*
 int hpl_column_sums(const float* rows, int64_t ld, int64_t n_rows, int64_t channels, float* sums, void* stream) {
     HPL_CHECK_ARG(rows && sums && ld >= channels && channels > 0);
     if (n_rows == 0) return 0;
-    long long blocks_y = (n_rows + 511) / 512;
-    if (blocks_y > 1024) blocks_y = 1024;
+    long long blocks_y = (n_rows + 127) / 128;
+    if (blocks_y > 4096) blocks_y = 4096;
     const long long rpb = (n_rows + blocks_y - 1) / blocks_y;
     dim3 g2((unsigned)((channels + 63) / 64), (unsigned)blocks_y);
-    column_sums_kernel<<<g2, 64, 0, as_stream(stream)>>>(rows, ld, n_rows, (int)channels, sums, rpb);
+    column_sums_kernel<<<g2, 256, 0, as_stream(stream)>>>(rows, ld, n_rows, (int)channels, sums, rpb);
     HPL_RETURN_LAST();
 }
 

@@ -143,12 +143,13 @@ __global__ void weight_image_kernel(const float* __restrict__ w, int filter_size
 }
 
 // ---------------------------------------------------------------------------------------------
-template <bool I64>
+template <bool I64, bool SCALED>
 __global__ void __launch_bounds__(kThreads, 2)
 gather_gemm_tc_kernel(const float* __restrict__ in, long long ld_in, long long n_in_rows, const void* __restrict__ nbr,
                       int filter_size, long long n_out_rows, int c_in, int c_out, int kb_per_tap,
                       const float* __restrict__ w_image, const float* __restrict__ bias, int act,
-                      float* __restrict__ out, long long ld_out, int out_cm, int n_main) {
+                      float* __restrict__ out, long long ld_out, int out_cm, int n_main,
+                      const float* __restrict__ row_scale) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], accum_bar;
@@ -182,7 +183,10 @@ gather_gemm_tc_kernel(const float* __restrict__ in, long long ld_in, long long n
         // ------------------------------------------------------------------ producers
         const int q = lane >> 3, r8 = lane & 7;              // 16-byte chunk of the 64-byte K block, row in group
         int row[2] = {-1, -1};
+        float rscale[2] = {1.f, 1.f};                        // density normalisation folded into the gather
         float4 pre[kPrefetch][2];
+        float pre_s[kPrefetch][2];                           // scale of each prefetched chunk (applied when consumed,
+                                                             // so the loads stay in flight)
 
         auto load_rows = [&](int f) {
 #pragma unroll
@@ -194,21 +198,24 @@ gather_gemm_tc_kernel(const float* __restrict__ in, long long ld_in, long long n
                     if (r >= n_in_rows) r = -1;
                 }
                 row[i] = r;
+                if constexpr (SCALED) rscale[i] = r >= 0 ? __ldg(row_scale + r) : 1.f;
             }
         };
-        auto issue = [&](int kb, float4* dst) {
+        auto issue = [&](int kb, float4* dst, float* sdst) {
             // rows of tap f must be current: callers walk kb in order, so refresh on tap change
             const int f = kb / kb_per_tap, c = (kb - f * kb_per_tap) * TK + 4 * q;
             if (kb % kb_per_tap == 0) load_rows(f);
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
+            for (int i = 0; i < 2; ++i) {
                 dst[i] = (row[i] >= 0 && c < c_in) ? __ldg(reinterpret_cast<const float4*>(in + (long long)row[i] * ld_in + c))
                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                if constexpr (SCALED) sdst[i] = rscale[i];
+            }
         };
 
 #pragma unroll
         for (int d = 0; d < kPrefetch; ++d)
-            if (d < n_kb) issue(d, pre[d]);
+            if (d < n_kb) issue(d, pre[d], pre_s[d]);
 
         for (int kb0 = 0; kb0 < n_kb; kb0 += kPrefetch) {
 #pragma unroll
@@ -219,8 +226,15 @@ gather_gemm_tc_kernel(const float* __restrict__ in, long long ld_in, long long n
                 const uint32_t phase = (kb / kStages) & 1;
                 float4 hi[2], lo[2];
 #pragma unroll
-                for (int i = 0; i < 2; ++i) split4(pre[d][i], hi[i], lo[i]);
-                if (kb + kPrefetch < n_kb) issue(kb + kPrefetch, pre[d]);          // refill this slot
+                for (int i = 0; i < 2; ++i) {
+                    float4 v = pre[d][i];
+                    if constexpr (SCALED) {
+                        const float sc = pre_s[d][i];
+                        v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+                    }
+                    split4(v, hi[i], lo[i]);
+                }
+                if (kb + kPrefetch < n_kb) issue(kb + kPrefetch, pre[d], pre_s[d]);   // refill this slot
                 if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);     // one poller per warp
                 __syncwarp();
                 const uint32_t a_hi = smem_base + stage * kStageBytes;
@@ -352,6 +366,7 @@ gather_gemm_tc_kernel(const float* __restrict__ in, long long ld_in, long long n
 // global read is 4 rows x 128 contiguous bytes per warp instruction.
 // One CTA = one 128-row M tile x one 64-column N tile x a contiguous vertex range; the partial
 // product leaves through fp32 RED.  Same 3xTF32 split and accumulator spreading as the forward.
+constexpr int kPrefetchW = 3;                                   // register budget: 3 operands per stage here
 constexpr int WG_MAIN = 3;                                     // hi.hi accumulators per CTA
 constexpr uint32_t kMnAtom = 512;                              // 32 MN elements x 4 K rows
 constexpr uint32_t kWA_SBO = (TM / 32) * kMnAtom;              // 2048: next 4 vertices of the A tile
@@ -377,7 +392,7 @@ template <bool I64>
 __global__ void __launch_bounds__(kThreads, 2)
 wgrad_tc_kernel(const float* __restrict__ in, long long ld_in, long long n_in_rows, const void* __restrict__ nbr,
                 int filter_size, long long n_out_rows, int c_in, int c_out, const float* __restrict__ dz, long long ld_dz,
-                float* __restrict__ dw, long long rows_per_split) {
+                float* __restrict__ dw, long long rows_per_split, const float* __restrict__ row_scale) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], accum_bar;
@@ -432,8 +447,9 @@ wgrad_tc_kernel(const float* __restrict__ in, long long ld_in, long long n_in_ro
         const uint32_t off_b = kgrp_b * kWB_SBO + atom_b * kMnAtom + swz;
         const bool b_live = o0 + n_b < c_out;
 
-        float4 pre[kPrefetch][3];
-        auto issue = [&](int kb, float4* dst) {
+        float4 pre[kPrefetchW][3];
+        float pre_s[kPrefetchW][2];
+        auto issue = [&](int kb, float4* dst, float* sdst) {
             const long long vb = v_lo + (long long)kb * TK;
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
@@ -445,26 +461,35 @@ wgrad_tc_kernel(const float* __restrict__ in, long long ld_in, long long n_in_ro
                 }
                 dst[i] = r >= 0 ? __ldg(reinterpret_cast<const float4*>(in + (long long)r * ld_in + ch[i]))
                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                sdst[i] = (row_scale != nullptr && r >= 0) ? __ldg(row_scale + r) : 1.f;
             }
             const long long v = vb + kk_b;
             dst[2] = (v < v_hi && b_live) ? __ldg(reinterpret_cast<const float4*>(dz + v * ld_dz + o0 + n_b))
                                           : make_float4(0.f, 0.f, 0.f, 0.f);
         };
 #pragma unroll
-        for (int d = 0; d < kPrefetch; ++d)
-            if (d < n_kb) issue(d, pre[d]);
+        for (int d = 0; d < kPrefetchW; ++d)
+            if (d < n_kb) issue(d, pre[d], pre_s[d]);
 
-        for (int kb0 = 0; kb0 < n_kb; kb0 += kPrefetch) {
+        for (int kb0 = 0; kb0 < n_kb; kb0 += kPrefetchW) {
 #pragma unroll
-            for (int d = 0; d < kPrefetch; ++d) {
+            for (int d = 0; d < kPrefetchW; ++d) {
                 const int kb = kb0 + d;
                 if (kb >= n_kb) break;
                 const int stage = kb % kStages;
                 const uint32_t phase = (kb / kStages) & 1;
                 float4 hi[3], lo[3];
 #pragma unroll
-                for (int i = 0; i < 3; ++i) split4(pre[d][i], hi[i], lo[i]);
-                if (kb + kPrefetch < n_kb) issue(kb + kPrefetch, pre[d]);
+                for (int i = 0; i < 2; ++i) {
+                    float4 v = pre[d][i];
+                    if (row_scale != nullptr) {
+                        const float sc = pre_s[d][i];
+                        v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+                    }
+                    split4(v, hi[i], lo[i]);
+                }
+                split4(pre[d][2], hi[2], lo[2]);
+                if (kb + kPrefetchW < n_kb) issue(kb + kPrefetchW, pre[d], pre_s[d]);
                 if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
                 __syncwarp();
                 const uint32_t a_hi = smem_base + stage * kStageBytes;
@@ -570,7 +595,8 @@ int64_t hpl_blur_gemm_tc_workspace(int64_t filter_size, int64_t c_in, int64_t c_
 
 int hpl_blur_gemm_tc(const float* in, int64_t ld_in, int64_t n_in_rows, const void* nbr, int idx64, int64_t filter_size,
                      int64_t n_out_rows, int64_t c_in, int64_t c_out, const float* w, const float* bias, int act,
-                     float* out, int64_t ld_out, int out_channel_major, float* workspace, void* stream) {
+                     float* out, int64_t ld_out, int out_channel_major, float* workspace, const float* row_scale,
+                     void* stream) {
     HPL_CHECK_ARG(in && w && out && workspace && c_in > 0 && c_out > 0 && filter_size > 0);
     HPL_CHECK_ARG(ld_in % 4 == 0 && ld_in >= c_in && ((uintptr_t)in & 15) == 0 && ((uintptr_t)workspace & 15) == 0);
     HPL_CHECK_ARG(nbr != nullptr || filter_size == 1);
@@ -584,28 +610,32 @@ int hpl_blur_gemm_tc(const float* in, int64_t ld_in, int64_t n_in_rows, const vo
 
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(gather_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        cudaFuncSetAttribute(gather_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaFuncSetAttribute(gather_gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaFuncSetAttribute(gather_gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaFuncSetAttribute(gather_gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaFuncSetAttribute(gather_gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         attr_set = true;
     }
     dim3 grid((unsigned)((n_out_rows + TM - 1) / TM), (unsigned)n_tiles);
     // accumulate steps of the hi.hi term per TMEM accumulator kept <= ~160 (truncation bias ~ steps * 2^-25)
     const long long steps = (long long)filter_size * kb_per_tap * (TK / 8);
     const int n_main = steps <= 160 ? 1 : (steps <= 480 ? 3 : 7);
-    if (idx64)
-        gather_gemm_tc_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, (int)c_in,
-                                                                        (int)c_out, kb_per_tap, workspace, bias, act, out, ld_out,
-                                                                        out_channel_major, n_main);
-    else
-        gather_gemm_tc_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, (int)c_in,
-                                                                         (int)c_out, kb_per_tap, workspace, bias, act, out, ld_out,
-                                                                         out_channel_major, n_main);
+#define HPL_LAUNCH_TC(I64, SC)                                                                                          \
+    gather_gemm_tc_kernel<I64, SC><<<grid, kThreads, kSmemBytes, s>>>(in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, \
+                                                                      (int)c_in, (int)c_out, kb_per_tap, workspace, bias, act, \
+                                                                      out, ld_out, out_channel_major, n_main, row_scale)
+    if (idx64) {
+        if (row_scale) HPL_LAUNCH_TC(true, true); else HPL_LAUNCH_TC(true, false);
+    } else {
+        if (row_scale) HPL_LAUNCH_TC(false, true); else HPL_LAUNCH_TC(false, false);
+    }
+#undef HPL_LAUNCH_TC
     HPL_RETURN_LAST();
 }
 
 int hpl_blur_wgrad_tc(const float* in, int64_t ld_in, int64_t n_in_rows, const void* nbr, int idx64, int64_t filter_size,
                       int64_t n_out_rows, int64_t c_in, int64_t c_out, const float* dz, int64_t ld_dz, float* dw, float* db,
-                      void* stream) {
+                      const float* row_scale, void* stream) {
     HPL_CHECK_ARG(in && dz && dw && c_in > 0 && c_out > 0 && filter_size > 0 && c_in % 4 == 0);
     HPL_CHECK_ARG(ld_in % 4 == 0 && ld_in >= c_in && ((uintptr_t)in & 15) == 0);
     HPL_CHECK_ARG(ld_dz % 4 == 0 && ld_dz >= c_out && ((uintptr_t)dz & 15) == 0 && ((uintptr_t)dw & 15) == 0);
@@ -634,10 +664,10 @@ int hpl_blur_wgrad_tc(const float* in, int64_t ld_in, int64_t n_in_rows, const v
     cudaStream_t s = as_stream(stream);
     if (idx64)
         wgrad_tc_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, (int)c_in,
-                                                                  (int)c_out, dz, ld_dz, dw, rows_per_split);
+                                                                  (int)c_out, dz, ld_dz, dw, rows_per_split, row_scale);
     else
         wgrad_tc_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, (int)c_in,
-                                                                   (int)c_out, dz, ld_dz, dw, rows_per_split);
+                                                                   (int)c_out, dz, ld_dz, dw, rows_per_split, row_scale);
     if (db != nullptr) return hpl_column_sums(dz, ld_dz, n_out_rows, c_out, db, stream);
     HPL_RETURN_LAST();
 }

@@ -279,8 +279,14 @@ int hpl_scatter_rows(const float* x, const float* bary, const void* off, int idx
 
 int hpl_normalize_rows(float* rows, int64_t ld, int64_t n_rows, int64_t channels, const float* wsum,
                        float* inv, void* stream) {
-    HPL_CHECK_ARG(rows && wsum && ld % 4 == 0 && ld >= channels && ((uintptr_t)rows & 15) == 0);
+    HPL_CHECK_ARG(wsum);
     if (n_rows == 0) return 0;
+    if (rows == nullptr) {   // reciprocal only
+        HPL_CHECK_ARG(inv == wsum);
+        reciprocal_kernel<<<blocks_for(n_rows, 256), 256, 0, as_stream(stream)>>>(inv, n_rows);
+        HPL_RETURN_LAST();
+    }
+    HPL_CHECK_ARG(ld % 4 == 0 && ld >= channels && ((uintptr_t)rows & 15) == 0);
     const int quads = (int)((channels + 3) / 4);
     normalize_rows_kernel<<<blocks_for(n_rows * quads, 256), 256, 0, as_stream(stream)>>>(rows, ld, n_rows, quads, wsum, inv);
     if (inv != nullptr && inv == wsum)

@@ -95,6 +95,17 @@ def normalize_rows_(rows, channels, wsum):
     return wsum
 
 
+def reciprocal_(wsum):
+    """In place: wsum <- 1/(wsum+1e-5), to be applied by the contraction kernels as ``row_scale``."""
+    _lib.call("hpl_normalize_rows", None, 0, wsum.numel(), 0, wsum.data_ptr(), wsum.data_ptr(), _stream())
+    return wsum
+
+
+def tc_path(c_in, precision=None):
+    """True when the tensor-core kernels (which can fold ``row_scale``) will run for this operand."""
+    return (DEFAULT_PRECISION if precision is None else precision) == 1 and c_in % 4 == 0
+
+
 def gather_rows(rows, channels, bary, off, scale=None, bias=None):
     """rows (H, ld) -> y (C, N)."""
     _f32(rows, "rows"); _f32(bary, "bary")
@@ -108,7 +119,7 @@ def gather_rows(rows, channels, bary, off, scale=None, bias=None):
 
 
 def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_major=False, precision=None,
-              tag="fwd"):
+              tag="fwd", row_scale=None):
     """out[v] = act(bias + sum_f x[nbr[f, v]] @ w[f]);  w (F, C, Co)."""
     _f32(x, "x"); _f32(w, "w")
     f, c, co = w.shape
@@ -131,8 +142,9 @@ def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_majo
         with _timed(tag):
             _lib.call("hpl_blur_gemm_tc", x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, f, n_out_rows, c, co,
                       w.data_ptr(), bias_ptr, act, out.data_ptr(), out.stride(0), int(out_channel_major),
-                      ws.data_ptr(), _stream())
+                      ws.data_ptr(), row_scale.data_ptr() if row_scale is not None else None, _stream())
     else:
+        assert row_scale is None, "row_scale is a tensor-core-path feature; normalise the rows instead"
         with _timed(tag):
             _lib.call("hpl_blur_gemm", x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, f, n_out_rows, c, co,
                       w.data_ptr(), bias_ptr, act, out.data_ptr(), out.stride(0), int(out_channel_major), 0,
@@ -140,7 +152,7 @@ def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_majo
     return out
 
 
-def blur_wgrad(x, c_in, nbr, n_out_rows, dz, c_out, filter_size, want_db=True, precision=None):
+def blur_wgrad(x, c_in, nbr, n_out_rows, dz, c_out, filter_size, want_db=True, precision=None, row_scale=None):
     """Returns dw (F, C, Co), db (Co)."""
     _f32(x, "x"); _f32(dz, "dz")
     if nbr is not None:
@@ -152,11 +164,14 @@ def blur_wgrad(x, c_in, nbr, n_out_rows, dz, c_out, filter_size, want_db=True, p
     db = torch.zeros(c_out, dtype=torch.float32, device=x.device) if want_db else None
     if precision is None:
         precision = DEFAULT_PRECISION
-    fn = "hpl_blur_wgrad_tc" if (precision == 1 and c_in % 4 == 0) else "hpl_blur_wgrad"
+    tc = precision == 1 and c_in % 4 == 0
+    assert tc or row_scale is None
+    extra = (row_scale.data_ptr() if row_scale is not None else None,) if tc else ()
+    fn = "hpl_blur_wgrad_tc" if tc else "hpl_blur_wgrad"
     with _timed("wgrad"):
         _lib.call(fn, x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, filter_size, n_out_rows,
                   c_in, c_out, dz.data_ptr(), dz.stride(0), dw.data_ptr(), db.data_ptr() if want_db else None,
-                  _stream())
+                  *extra, _stream())
     return dw, db
 
 

@@ -58,7 +58,8 @@ int hpl_scatter_rows(const float* x, const float* bary, const void* off, int idx
                      void* stream);
 
 /* Density normalisation (bilateralNN.py:185-186):  inv[v] = 1/(wsum[v] + 1e-5),
- * rows[v, :] *= inv[v].  inv may alias wsum. */
+ * rows[v, :] *= inv[v].  inv may alias wsum.  rows == NULL: only the reciprocal is computed (the
+ * tensor-core contraction applies it while gathering, see row_scale). */
 int hpl_normalize_rows(float* rows, int64_t ld, int64_t n_rows, int64_t channels,
                        const float* wsum, float* inv, void* stream);
 
@@ -88,12 +89,15 @@ int hpl_blur_gemm(const float* in, int64_t ld_in, int64_t n_in_rows, const void*
 /* Same contract as hpl_blur_gemm on the tcgen05 tensor cores with 3xTF32 error compensation
  * (fp32-level accuracy: every operand is split hi + lo in TF32, three MMAs per K step, fp32
  * accumulation in tensor memory).  `workspace` holds the pre-split weight image and must be
- * hpl_blur_gemm_tc_workspace(F, C, Co) bytes, 16-byte aligned; it is written by this call. */
+ * hpl_blur_gemm_tc_workspace(F, C, Co) bytes, 16-byte aligned; it is written by this call.
+ * row_scale (n_in_rows floats, may be NULL): every gathered row r is multiplied by row_scale[r]
+ * on the fly -- the density normalisation 1/(wsum+1e-5) of bilateralNN.py:185-186 without a
+ * separate pass over the lattice. */
 int64_t hpl_blur_gemm_tc_workspace(int64_t filter_size, int64_t c_in, int64_t c_out);
 int hpl_blur_gemm_tc(const float* in, int64_t ld_in, int64_t n_in_rows, const void* nbr, int idx64,
                      int64_t filter_size, int64_t n_out_rows, int64_t c_in, int64_t c_out,
                      const float* w, const float* bias, int act, float* out, int64_t ld_out,
-                     int out_channel_major, float* workspace, void* stream);
+                     int out_channel_major, float* workspace, const float* row_scale, void* stream);
 
 /* Weight gradient of the layer above:
  *   dw[f, c, o] += sum_v in[nbr[f,v], c] * dz[v, o]        db[o] += sum_v dz[v, o]
@@ -104,10 +108,11 @@ int hpl_blur_wgrad(const float* in, int64_t ld_in, int64_t n_in_rows, const void
                    const float* dz, int64_t ld_dz, float* dw, float* db, void* stream);
 
 /* Same contract as hpl_blur_wgrad on the tcgen05 tensor cores (3xTF32, see hpl_blur_gemm_tc).
- * Requires c_in % 4 == 0. */
+ * Requires c_in % 4 == 0.  row_scale as in hpl_blur_gemm_tc. */
 int hpl_blur_wgrad_tc(const float* in, int64_t ld_in, int64_t n_in_rows, const void* nbr, int idx64,
                       int64_t filter_size, int64_t n_out_rows, int64_t c_in, int64_t c_out,
-                      const float* dz, int64_t ld_dz, float* dw, float* db, void* stream);
+                      const float* dz, int64_t ld_dz, float* dw, float* db, const float* row_scale,
+                      void* stream);
 
 /* sums[c] += sum_v rows[v, c]  (conv bias gradients). rows (n_rows, ld) vertex-major. */
 int hpl_column_sums(const float* rows, int64_t ld, int64_t n_rows, int64_t channels, float* sums,

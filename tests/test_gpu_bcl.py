@@ -138,3 +138,31 @@ def test_linearity_and_null_vertex():
         y = mod(a, bary, off, torch.full_like(nbr, -1), bary, off)
         want = mod.blur_conv[0].bias[None, :, None] * bary.sum(1, keepdim=True)
         assert_close(y, want.expand_as(y), "null vertex")
+
+
+def test_fused_normalisation_matches_unfused():
+    # row_scale path of the tensor-core kernels (normalisation applied while gathering)
+    import hplflownet_b200.bilateralNN as B
+    d = _lattice(3000, 11, 1.0)
+    bary, off, nbr = [d[k].to(DEV) for k in ("pc1_barycentric", "pc1_lattice_offset", "pc1_blur_neighbors")]
+    torch.manual_seed(3)
+    mod = hpl.BilateralConvFlex(3, 1, 32, [48, 16], "cuda", use_bias=True, use_leaky=True, use_norm=True,
+                                do_splat=True, do_slice=True, last_relu=False, chunk_size=-1).to(DEV)
+    feat = torch.randn(1, 32, 3000, device=DEV)
+    gy = torch.randn(1, 16, 3000, device=DEV)
+    res = []
+    for fuse in (False, True):
+        B.FUSE_NORMALISATION = fuse
+        try:
+            f = feat.clone().requires_grad_(True)
+            for p in mod.parameters():
+                p.grad = None
+            y = mod(f, bary, off, nbr, bary, off)
+            y.backward(gy)
+            res.append((y.detach(), f.grad, [p.grad.clone() for p in mod.parameters()]))
+        finally:
+            B.FUSE_NORMALISATION = False
+    assert_close(res[1][0], res[0][0], "output")
+    assert_close_grad(res[1][1], res[0][1], "grad_features")
+    for a, b in zip(res[1][2], res[0][2]):
+        assert_close_grad(a, b, "param grad")

@@ -314,7 +314,7 @@ def run_ours(args):
     # ---- roofline of the dominant kernel: the blur gather-GEMM (forward launch), tcgen05 3xTF32.
     # achieved = algorithmic FLOPs (2*F*C*Co per vertex) / CUDA-event duration on the launch
     # stream; peak = measured dense bf16 tensor throughput (MEASURED_PEAKS.json, burst).  A 3xTF32
-    # contraction issues 3 TF32 MMAs (half the bf16 rate) per algorithmic MAC, so its ceiling is peak/6.
+    # contraction issues 3 MMAs per algorithmic MAC: ceiling peak/3 in FP16 (3xFP16), peak/6 in TF32.
     peaks = measured_peaks()
     by_tag = {}
     for tag, a, b in gemm_events:
@@ -325,13 +325,14 @@ def run_ours(args):
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
     fb, bb = algorithmic_bytes(n_tot, h_tot, CHANNELS, CHANNELS)
     all_gemm_ms = sum(a.elapsed_time(b) for _, a, b in gemm_events) / args.steps
-    engine = "tcgen05 3xTF32" if ops.DEFAULT_PRECISION == 1 else "fp32 CUDA-core FMA"
+    engine = {2: "tcgen05 3xFP16 (scaled hi/lo split)", 1: "tcgen05 3xTF32", 0: "fp32 CUDA-core FMA"}[ops.DEFAULT_PRECISION]
+    kname = {2: "gather_gemm_f16_kernel", 1: "gather_gemm_tc_kernel", 0: "gather_gemm_kernel"}[ops.DEFAULT_PRECISION]
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
         "frac": achieved / peaks["bf16_tflops"], "traffic": NCU_TRAFFIC_BYTES, "peak_source": peaks["source"],
-        "kernel": "gather_gemm_tc_kernel (blur forward, %s)" % engine,
+        "kernel": "%s (blur forward, %s)" % (kname, engine),
         "kernel_ms": gemm_ms, "kernel_ms_by_role": avg,
-        "frac_of_3xtf32_ceiling": achieved / (peaks["bf16_tflops"] / 6.0),
+        "frac_of_3_mma_ceiling": achieved / (peaks["bf16_tflops"] / (3.0 if ops.DEFAULT_PRECISION == 2 else 6.0)),
         "kernel_algorithmic_bytes": blur_fwd_bytes(h_tot, CHANNELS, CHANNELS),
         "kernel_algorithmic_gbs": blur_fwd_bytes(h_tot, CHANNELS, CHANNELS) / (gemm_ms * 1e-3) / 1e9,
         "contraction_share_of_step": all_gemm_ms / (ms / args.steps),

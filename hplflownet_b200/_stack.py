@@ -12,21 +12,26 @@ def forward(x, c_in, n_rows, layers, first_nbr=None, last_channel_major=False, f
     vertex-major output -- unless the last layer is written channel-major directly (only when it has
     no activation), in which case it is returned as out_cm and not kept in xs."""
     xs, chans, out_cm = [x], [c_in], None
+    amaxs = []                     # max|input| of every layer (3xFP16 path), reused by the weight gradient
     for l, (w, b, act) in enumerate(layers):
         last = l == len(layers) - 1
         direct_cm = last and last_channel_major and act == ops.ACT_NONE
+        scale = first_row_scale if l == 0 else None
+        amax = ops.absmax(xs[-1]) if (ops.DEFAULT_PRECISION == 2 and scale is None) else None
+        amaxs.append(amax)
         y = ops.blur_gemm(xs[-1], chans[-1], first_nbr if l == 0 else None, n_rows, w, b,
-                          act, out_channel_major=direct_cm, row_scale=first_row_scale if l == 0 else None)
+                          act, out_channel_major=direct_cm, row_scale=scale, x_amax=amax)
         if direct_cm:
             out_cm = y
         else:
             xs.append(y)
         chans.append(w.size(2))
+    forward.last_amaxs = amaxs
     return xs, chans, out_cm
 
 
 def backward(dx, xs, chans, layers, n_rows, first_nbr, first_nbr_t, need_input_grad, need_param_grad,
-             first_row_scale=None):
+             first_row_scale=None, amaxs=None):
     """dx: gradient w.r.t. the stack's (post-activation) output, vertex-major, modified in place.
     first_nbr_t: callable returning the transposed table of the first layer (built lazily).
     Returns (dx_in or None, [(dw (F, C, Co), db (Co)) or None per layer])."""
@@ -36,14 +41,16 @@ def backward(dx, xs, chans, layers, n_rows, first_nbr, first_nbr_t, need_input_g
         if act != ops.ACT_NONE:
             ops.act_backward_(dx, xs[l + 1], chans[l + 1], act)
         tbl = first_nbr if l == 0 else None
+        dz_amax = ops.absmax(dx) if ops.DEFAULT_PRECISION == 2 else None      # shared by wgrad and dgrad
         if need_param_grad[l]:
             grads[l] = ops.blur_wgrad(xs[l], chans[l], tbl, n_rows, dx, chans[l + 1], w.size(0), want_db=b is not None,
-                                      row_scale=first_row_scale if l == 0 else None)
+                                      row_scale=first_row_scale if l == 0 else None,
+                                      x_amax=amaxs[l] if amaxs else None, dz_amax=dz_amax)
         if l > 0 or need_input_grad:
             wd = w.transpose(1, 2).contiguous()                       # (F, Co, C)
             tbl_t = first_nbr_t() if (l == 0 and first_nbr is not None) else None
             n_in = xs[l].size(0)
-            dx = ops.blur_gemm(dx, chans[l + 1], tbl_t, n_in, wd, None, ops.ACT_NONE, tag="dgrad")
+            dx = ops.blur_gemm(dx, chans[l + 1], tbl_t, n_in, wd, None, ops.ACT_NONE, tag="dgrad", x_amax=dz_amax)
         else:
             dx = None
     return dx, grads

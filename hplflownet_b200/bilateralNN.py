@@ -116,6 +116,7 @@ class _BCLFunction(torch.autograd.Function):
 
         ctx.cfg, ctx.chans, ctx.h = cfg, chans, h
         ctx.xs, ctx.layers, ctx.inv, ctx.scale0 = xs, layers, inv, scale0
+        ctx.amaxs = _stack.forward.last_amaxs
         ctx.idx = (bary_i, off_i, nbr2, bary_o, off_o)
         ctx.has_slice_bias = slice_bias is not None
         ctx.param_shapes = [p.shape for p in params]
@@ -138,7 +139,7 @@ class _BCLFunction(torch.autograd.Function):
         need_feat = ctx.needs_input_grad[1]
         need_param = [ctx.needs_input_grad[8 + 2 * l] or ctx.needs_input_grad[9 + 2 * l] for l in range(len(layers))]
         dx, pg = _stack.backward(dx, xs, chans, layers, h, nbr2, lambda: ops.transpose_table(nbr2, h),
-                                 need_feat, need_param, first_row_scale=ctx.scale0)
+                                 need_feat, need_param, first_row_scale=ctx.scale0, amaxs=ctx.amaxs)
         grads = []
         for l, g_l in enumerate(pg):
             if g_l is None:

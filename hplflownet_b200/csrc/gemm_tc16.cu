@@ -1,0 +1,580 @@
+// Gather-GEMM and weight gradient on tcgen05 with a scaled FP16 hi/lo split ("3xFP16").
+//
+// Same contraction and the same fp32-level accuracy target as gemm_tc.cu (3xTF32), but every operand
+// element travels as two 2-byte halves instead of two 4-byte TF32 words.  Both kernels are bound by
+// the SM's shared-memory data pipe (operand staging of a *gathered* A, ncu: ~80 % busy, tensor pipe
+// ~20 %), so halving the operand bytes -- and using kind::f16 MMAs with K = 16 -- is what moves them.
+//
+//   x / s = hi + lo * 2^-11 (+ <= 2^-22 |x / s|),   hi = fp16(x / s),   lo = fp16((x / s - hi) * 2^11)
+//   s = 2^(floor(log2 max|x|) - 13): a per-tensor power of two that places the largest element in
+//   [2^13, 2^14), so fp16's 5-bit exponent covers 2^-28 of the tensor's range at full relative precision
+//   (smaller elements keep an absolute error <= 2^-39 of the maximum).  The maximum is a device scalar
+//   produced by hpl_absmax -- no host synchronisation.
+//   a.b = s_a s_b [ hi_a.hi_b + 2^-11 (hi_a.lo_b + lo_a.hi_b) ]   (lo.lo dropped: 2^-22 relative)
+// fp16 x fp16 products are exact in the fp32 accumulator; the cross terms and the main term use separate
+// TMEM accumulators and the main term is spread over 1/3/7 accumulators by K range (truncation bias, see
+// gemm_tc.cu).  Layouts: forward operands K-major no-swizzle, weight-gradient operands MN-major no-swizzle
+// (valid for 16-bit elements; address maps verified with tools/umma_probe.cu).
+#include <cuda_fp16.h>
+
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int TM = 128, TN = 64;
+constexpr int TK = 32;                       // K elements per stage = 2 MMAs of K = 16
+constexpr int kStages = 4;
+constexpr int kProducerWarps = 8;
+constexpr int kThreads = kProducerWarps * 32 + 64;
+constexpr int kPrefetch = 2;                 // stages of gathered rows in flight per producer thread
+constexpr int kAHalf = TM * TK * 2;          // 8 KB
+constexpr int kBHalf = TN * TK * 2;          // 4 KB
+constexpr int kStageBytes = 2 * kAHalf + 2 * kBHalf;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+constexpr uint32_t kA_LBO = TM * 16, kB_LBO = TN * 16, kSBO = 128;
+constexpr uint32_t kIdescK = instr_desc(0, TM, TN, 0, 0);
+constexpr uint32_t kIdescMN = instr_desc(0, TM, TN, 1, 1);
+constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
+
+__device__ __forceinline__ void scale_from_amax(uint32_t bits, float& scale, float& inv_scale) {
+    int e = (int)((bits >> 23) & 0xff) - 127;
+    if (bits == 0) e = 13;
+    int se = e - 13;
+    se = se < -100 ? -100 : (se > 100 ? 100 : se);
+    scale = __uint_as_float((uint32_t)(se + 127) << 23);
+    inv_scale = __uint_as_float((uint32_t)(127 - se) << 23);
+}
+
+// 8 consecutive fp32 -> 8 hi halves + 8 lo halves (4 x b32 each)
+__device__ __forceinline__ void split8(const float4 a, const float4 b, float inv_s, uint32_t* hi, uint32_t* lo) {
+    const float x[8] = {a.x * inv_s, a.y * inv_s, a.z * inv_s, a.w * inv_s, b.x * inv_s, b.y * inv_s, b.z * inv_s, b.w * inv_s};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 h = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+        const float2 f = __half22float2(h);
+        const __half2 l = __floats2half2_rn((x[2 * i] - f.x) * kLoScale, (x[2 * i + 1] - f.y) * kLoScale);
+        hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+}
+
+// ------------------------------------------------------------------------------------ absmax
+__global__ void absmax_kernel(const float4* __restrict__ x, long long n4, uint32_t* __restrict__ out) {
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(x + i);
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));   // non-negative floats order as uints
+}
+__global__ void absmax_tail_kernel(const float* __restrict__ x, long long lo, long long n, uint32_t* __restrict__ out) {
+    const long long i = lo + threadIdx.x;
+    if (i < n) {
+        const float m = fabsf(x[i]);
+        if (m > 0.f) atomicMax(out, __float_as_uint(m));
+    }
+}
+
+// ------------------------------------------------------------------------------ weight image
+// w (F, C, Co) fp32 -> per (N tile, K block of 32) [hi 4 KB | lo 4 KB] in the shared-memory layout.
+__global__ void weight_image16_kernel(const float* __restrict__ w, int filter_size, int c_in, int c_out, int kb_per_tap,
+                                      const uint32_t* __restrict__ w_amax, uint8_t* __restrict__ image) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int chunks = TN * (TK / 8);                                  // 256 16-byte chunks per K block
+    const long long n_kb = (long long)filter_size * kb_per_tap;
+    const long long n_tiles = (c_out + TN - 1) / TN;
+    if (t >= n_tiles * n_kb * chunks) return;
+    float s, inv_s;
+    scale_from_amax(*w_amax, s, inv_s);
+    const int chunk = (int)(t % chunks);
+    const long long blk = t / chunks;
+    const long long kb = blk % n_kb, tile = blk / n_kb;
+    const int f = (int)(kb / kb_per_tap), c0 = (int)(kb % kb_per_tap) * TK;
+    const int n = chunk & (TN - 1), kc = chunk / TN;
+    const int o = (int)tile * TN + n;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = c0 + 8 * kc + i;
+        v[i] = (c < c_in && o < c_out) ? __ldg(w + ((long long)f * c_in + c) * c_out + o) : 0.f;
+    }
+    uint32_t hi[4], lo[4];
+    split8(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]), inv_s, hi, lo);
+    uint8_t* dst = image + blk * (2 * kBHalf) + kc * (TN * 16) + (n >> 3) * 128 + (n & 7) * 16;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(dst + kBHalf) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// ------------------------------------------------------------------------------ forward / dgrad
+template <bool I64>
+__global__ void __launch_bounds__(kThreads, 2)
+gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_rows, const void* __restrict__ nbr,
+                       int filter_size, long long n_out_rows, int c_in, int c_out, int kb_per_tap,
+                       const uint8_t* __restrict__ w_image, const float* __restrict__ bias, int act, float* __restrict__ out,
+                       long long ld_out, int out_cm, int n_main, const uint32_t* __restrict__ in_amax,
+                       const uint32_t* __restrict__ w_amax) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], accum_bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long m0 = (long long)blockIdx.x * TM;
+    const int n_tile = blockIdx.y;
+    const int n_kb = filter_size * kb_per_tap;
+    const uint32_t tmem_cols = (uint32_t)(TN * (n_main + 1));
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], kProducerWarps + 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&accum_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == kProducerWarps) tmem_alloc(&tmem_slot, tmem_cols);
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_d = tmem_slot;
+    const uint32_t smem_base = smem_u32(smem);
+    float s_in, inv_in, s_w, inv_w;
+    scale_from_amax(__ldg(in_amax), s_in, inv_in);
+    scale_from_amax(__ldg(w_amax), s_w, inv_w);
+
+    if (warp < kProducerWarps) {
+        const int q = lane >> 3, r8 = lane & 7;          // 32-byte source granule (8 K elements) / row in group
+        int row[2] = {-1, -1};
+        float4 pre[kPrefetch][2][2];
+        auto load_rows = [&](int f) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const long long v = m0 + (warp * 2 + i) * 8 + r8;
+                int r = -1;
+                if (v < n_out_rows) {
+                    r = nbr != nullptr ? load_idx<I64>(nbr, (long long)f * n_out_rows + v) : (int)v;
+                    if (r >= n_in_rows) r = -1;
+                }
+                row[i] = r;
+            }
+        };
+        auto issue = [&](int kb, float4 (*dst)[2]) {
+            const int f = kb / kb_per_tap, c = (kb - f * kb_per_tap) * TK + 8 * q;
+            if (kb % kb_per_tap == 0) load_rows(f);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const float* p = in + (long long)row[i] * ld_in + c;
+                dst[i][0] = (row[i] >= 0 && c < c_in) ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                dst[i][1] = (row[i] >= 0 && c + 4 < c_in) ? __ldg(reinterpret_cast<const float4*>(p + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+#pragma unroll
+        for (int d = 0; d < kPrefetch; ++d)
+            if (d < n_kb) issue(d, pre[d]);
+
+        for (int kb0 = 0; kb0 < n_kb; kb0 += kPrefetch) {
+#pragma unroll
+            for (int d = 0; d < kPrefetch; ++d) {
+                const int kb = kb0 + d;
+                if (kb >= n_kb) break;
+                const int stage = kb % kStages;
+                const uint32_t phase = (kb / kStages) & 1;
+                uint32_t hi[2][4], lo[2][4];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) split8(pre[d][i][0], pre[d][i][1], inv_in, hi[i], lo[i]);
+                if (kb + kPrefetch < n_kb) issue(kb + kPrefetch, pre[d]);
+                if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
+                __syncwarp();
+                const uint32_t a_hi = smem_base + stage * kStageBytes;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const uint32_t off = q * (TM * 16) + (warp * 2 + i) * 128 + r8 * 16;
+                    sts128(a_hi + off, hi[i][0], hi[i][1], hi[i][2], hi[i][3]);
+                    sts128(a_hi + kAHalf + off, lo[i][0], lo[i][1], lo[i][2], lo[i][3]);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_bar[stage]);
+            }
+        }
+    } else if (warp == kProducerWarps) {
+        if (lane == 0) {
+            int last_g = -1;
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int stage = kb % kStages;
+                const int g = (int)((long long)kb * n_main / n_kb);
+                const uint32_t tmem_main = tmem_d + (uint32_t)(TN * (1 + g));
+                mbar_wait(&full_bar[stage], (kb / kStages) & 1);
+                fence_after();
+                const uint32_t a_hi = smem_base + stage * kStageBytes;
+                const uint32_t a_lo = a_hi + kAHalf, b_hi = a_hi + 2 * kAHalf, b_lo = b_hi + kBHalf;
+#pragma unroll
+                for (int j = 0; j < TK / 16; ++j) {
+                    const uint64_t dah = smem_desc(a_hi + j * 2 * kA_LBO, kA_LBO, kSBO);
+                    const uint64_t dal = smem_desc(a_lo + j * 2 * kA_LBO, kA_LBO, kSBO);
+                    const uint64_t dbh = smem_desc(b_hi + j * 2 * kB_LBO, kB_LBO, kSBO);
+                    const uint64_t dbl = smem_desc(b_lo + j * 2 * kB_LBO, kB_LBO, kSBO);
+                    umma_f16(tmem_d, dal, dbh, kIdescK, (kb | j) != 0);
+                    umma_f16(tmem_d, dah, dbl, kIdescK, 1);
+                    umma_f16(tmem_main, dah, dbh, kIdescK, g == last_g);
+                    last_g = g;
+                }
+                umma_commit(&empty_bar[stage]);
+            }
+            umma_commit(&accum_bar);
+        }
+    } else {
+        if (lane == 0) {
+            const uint8_t* src = w_image + (long long)n_tile * n_kb * (2 * kBHalf);
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int stage = kb % kStages;
+                mbar_wait(&empty_bar[stage], ((kb / kStages) & 1) ^ 1);
+                mbar_arrive_expect_tx(&full_bar[stage], 2 * kBHalf);
+                bulk_load(smem_base + stage * kStageBytes + 2 * kAHalf, src + (long long)kb * (2 * kBHalf), 2 * kBHalf, &full_bar[stage]);
+            }
+        }
+    }
+
+    if (warp < 4) {
+        mbar_wait(&accum_bar, 0);
+        fence_after();
+        const long long m = m0 + warp * 32 + lane;
+        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
+        const int o0 = n_tile * TN;
+        const float s_ab = s_in * s_w;
+#pragma unroll 1
+        for (int cb = 0; cb < TN; cb += 16) {
+            float sum[16];
+            uint32_t v[16];
+            tmem_ld16(taddr + cb, v);                                       // cross terms
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sum[j] = __uint_as_float(v[j]) * kLoInv;
+            for (int g = 1; g <= n_main; ++g) {
+                tmem_ld16(taddr + g * TN + cb, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sum[j] += __uint_as_float(v[j]);
+            }
+            if (m < n_out_rows) {
+                float y[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int o = o0 + cb + j;
+                    const float b = (bias != nullptr && o < c_out) ? __ldg(bias + o) : 0.f;
+                    y[j] = apply_act(fmaf(sum[j], s_ab, b), act);
+                }
+                if (!out_cm) {
+                    float* p = out + m * ld_out + o0 + cb;
+                    if (o0 + cb + 15 < c_out && (ld_out & 3) == 0 && ((uintptr_t)out & 15) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(p + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (o0 + cb + j < c_out) p[j] = y[j];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (o0 + cb + j < c_out) out[(long long)(o0 + cb + j) * ld_out + m] = y[j];
+                }
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == kProducerWarps) {
+        fence_after();
+        tmem_dealloc(tmem_d, tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------ weight gradient
+// dw[(f,c), o] += sum_v in[nbr[f,v], c] * dz[v, o];  both operands MN-major no-swizzle fp16:
+//   element (m, k) at (k / 8) * LBO + (m / 8) * 128 + (k % 8) * 16 + (m % 8) * 2
+constexpr int WG_MAIN = 3;
+constexpr uint32_t kWA_LBO = (TM / 8) * 128;      // 2048: next 8 vertices of the A tile
+constexpr uint32_t kWB_LBO = (TN / 8) * 128;      // 1024
+
+template <bool I64>
+__global__ void __launch_bounds__(kThreads, 2)
+wgrad_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_rows, const void* __restrict__ nbr,
+                 int filter_size, long long n_out_rows, int c_in, int c_out, const float* __restrict__ dz, long long ld_dz,
+                 float* __restrict__ dw, long long rows_per_split, const uint32_t* __restrict__ in_amax,
+                 const uint32_t* __restrict__ dz_amax) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], accum_bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * TM, o0 = blockIdx.z * TN;
+    const int m_total = filter_size * c_in;
+    const long long v_lo = rows_per_split * blockIdx.x;
+    const long long v_hi = min(n_out_rows, v_lo + rows_per_split);
+    const int n_kb = v_lo < v_hi ? (int)((v_hi - v_lo + TK - 1) / TK) : 0;
+    const uint32_t tmem_cols = (uint32_t)(TN * (WG_MAIN + 1));
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], kProducerWarps);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&accum_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == kProducerWarps) tmem_alloc(&tmem_slot, tmem_cols);
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_d = tmem_slot;
+    const uint32_t smem_base = smem_u32(smem);
+    float s_in, inv_in, s_dz, inv_dz;
+    scale_from_amax(__ldg(in_amax), s_in, inv_in);
+    scale_from_amax(__ldg(dz_amax), s_dz, inv_dz);
+
+    if (warp < kProducerWarps) {
+        const int q = lane >> 3, r8 = lane & 7;           // MN chunk inside the warp task / vertex inside the K group
+        int tap[2], ch[2], kk_a[2];
+        uint32_t off_a[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int wt = warp * 2 + i;
+            const int kgrp = wt & 3, mc = (wt >> 2) * 4 + q;          // 4 K groups x 16 chunks of 8 rows of M
+            kk_a[i] = kgrp * 8 + r8;
+            const int m = m0 + mc * 8;
+            tap[i] = m < m_total ? m / c_in : -1;
+            ch[i] = m < m_total ? m - tap[i] * c_in : 0;
+            off_a[i] = kgrp * kWA_LBO + mc * 128 + r8 * 16;
+        }
+        const int kgrp_b = warp & 3, nc = (warp >> 2) * 4 + q;        // 4 K groups x 8 chunks of N
+        const int kk_b = kgrp_b * 8 + r8, n_b = nc * 8;
+        const uint32_t off_b = kgrp_b * kWB_LBO + nc * 128 + r8 * 16;
+
+        float4 pre[kPrefetch][3][2];
+        auto issue = [&](int kb, float4 (*dst)[2]) {
+            const long long vb = v_lo + (long long)kb * TK;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const long long v = vb + kk_a[i];
+                int r = -1;
+                if (v < v_hi && tap[i] >= 0) {
+                    r = nbr != nullptr ? load_idx<I64>(nbr, (long long)tap[i] * n_out_rows + v) : (int)v;
+                    if (r >= n_in_rows) r = -1;
+                }
+                const float* p = in + (long long)r * ld_in + ch[i];
+                dst[i][0] = r >= 0 ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                dst[i][1] = r >= 0 ? __ldg(reinterpret_cast<const float4*>(p + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            const long long v = vb + kk_b;
+            const float* pz = dz + v * ld_dz + o0 + n_b;
+            dst[2][0] = (v < v_hi && o0 + n_b < c_out) ? __ldg(reinterpret_cast<const float4*>(pz)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            dst[2][1] = (v < v_hi && o0 + n_b + 4 < c_out) ? __ldg(reinterpret_cast<const float4*>(pz + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+#pragma unroll
+        for (int d = 0; d < kPrefetch; ++d)
+            if (d < n_kb) issue(d, pre[d]);
+
+        for (int kb0 = 0; kb0 < n_kb; kb0 += kPrefetch) {
+#pragma unroll
+            for (int d = 0; d < kPrefetch; ++d) {
+                const int kb = kb0 + d;
+                if (kb >= n_kb) break;
+                const int stage = kb % kStages;
+                const uint32_t phase = (kb / kStages) & 1;
+                uint32_t hi[3][4], lo[3][4];
+                split8(pre[d][0][0], pre[d][0][1], inv_in, hi[0], lo[0]);
+                split8(pre[d][1][0], pre[d][1][1], inv_in, hi[1], lo[1]);
+                split8(pre[d][2][0], pre[d][2][1], inv_dz, hi[2], lo[2]);
+                if (kb + kPrefetch < n_kb) issue(kb + kPrefetch, pre[d]);
+                if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
+                __syncwarp();
+                const uint32_t a_hi = smem_base + stage * kStageBytes;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    sts128(a_hi + off_a[i], hi[i][0], hi[i][1], hi[i][2], hi[i][3]);
+                    sts128(a_hi + kAHalf + off_a[i], lo[i][0], lo[i][1], lo[i][2], lo[i][3]);
+                }
+                sts128(a_hi + 2 * kAHalf + off_b, hi[2][0], hi[2][1], hi[2][2], hi[2][3]);
+                sts128(a_hi + 2 * kAHalf + kBHalf + off_b, lo[2][0], lo[2][1], lo[2][2], lo[2][3]);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_bar[stage]);
+            }
+        }
+    } else if (warp == kProducerWarps) {
+        if (lane == 0) {
+            int last_g = -1;
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int stage = kb % kStages;
+                const int g = (int)((long long)kb * WG_MAIN / n_kb);
+                const uint32_t tmem_main = tmem_d + (uint32_t)(TN * (1 + g));
+                mbar_wait(&full_bar[stage], (kb / kStages) & 1);
+                fence_after();
+                const uint32_t a_hi = smem_base + stage * kStageBytes;
+                const uint32_t a_lo = a_hi + kAHalf, b_hi = a_hi + 2 * kAHalf, b_lo = b_hi + kBHalf;
+#pragma unroll
+                for (int j = 0; j < TK / 16; ++j) {                      // one MMA = 2 K groups of 8 vertices
+                    const uint64_t dah = smem_desc(a_hi + j * 2 * kWA_LBO, kWA_LBO, kSBO);
+                    const uint64_t dal = smem_desc(a_lo + j * 2 * kWA_LBO, kWA_LBO, kSBO);
+                    const uint64_t dbh = smem_desc(b_hi + j * 2 * kWB_LBO, kWB_LBO, kSBO);
+                    const uint64_t dbl = smem_desc(b_lo + j * 2 * kWB_LBO, kWB_LBO, kSBO);
+                    umma_f16(tmem_d, dal, dbh, kIdescMN, (kb | j) != 0);
+                    umma_f16(tmem_d, dah, dbl, kIdescMN, 1);
+                    umma_f16(tmem_main, dah, dbh, kIdescMN, g == last_g);
+                    last_g = g;
+                }
+                umma_commit(&empty_bar[stage]);
+            }
+            umma_commit(&accum_bar);
+        }
+    }
+
+    if (warp < 4 && n_kb > 0) {
+        mbar_wait(&accum_bar, 0);
+        fence_after();
+        const int m = m0 + warp * 32 + lane;
+        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
+        const float s_ab = s_in * s_dz;
+#pragma unroll 1
+        for (int cb = 0; cb < TN; cb += 16) {
+            float sum[16];
+            uint32_t v[16];
+            tmem_ld16(taddr + cb, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sum[j] = __uint_as_float(v[j]) * kLoInv;
+            for (int g = 1; g <= WG_MAIN; ++g) {
+                const int first_kb = ((g - 1) * n_kb + WG_MAIN - 1) / WG_MAIN;     // accumulator used iff some kb maps to it
+                if (first_kb >= n_kb || (int)((long long)first_kb * WG_MAIN / n_kb) != g - 1) continue;
+                tmem_ld16(taddr + g * TN + cb, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sum[j] += __uint_as_float(v[j]);
+            }
+            if (m < m_total) {
+                float* p = dw + (long long)m * c_out + o0 + cb;
+                if (o0 + cb + 15 < c_out && (c_out & 3) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        red_add_f32x4(p + j, make_float4(sum[j] * s_ab, sum[j + 1] * s_ab, sum[j + 2] * s_ab, sum[j + 3] * s_ab));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (o0 + cb + j < c_out) atomicAdd(p + j, sum[j] * s_ab);
+                }
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == kProducerWarps) {
+        fence_after();
+        tmem_dealloc(tmem_d, tmem_cols);
+    }
+}
+
+void set_attrs() {
+    static bool done = false;
+    if (done) return;
+    cudaFuncSetAttribute(gather_gemm_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaFuncSetAttribute(gather_gemm_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaFuncSetAttribute(wgrad_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaFuncSetAttribute(wgrad_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    done = true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hpl_absmax(const float* x, int64_t count, uint32_t* out_bits, void* stream) {
+    HPL_CHECK_ARG(out_bits && (x || count == 0) && ((uintptr_t)x & 15) == 0);
+    cudaStream_t s = as_stream(stream);
+    cudaError_t e = cudaMemsetAsync(out_bits, 0, 4, s);
+    if (e != cudaSuccess) return (int)e;
+    if (count == 0) return 0;
+    const long long n4 = count / 4;
+    if (n4 > 0) {
+        long long blocks = (n4 + 255) / 256;
+        const long long cap = 8LL * num_sms();
+        if (blocks > cap) blocks = cap;
+        absmax_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(x), n4, out_bits);
+    }
+    if (count % 4) absmax_tail_kernel<<<1, 32, 0, s>>>(x, n4 * 4, count, out_bits);
+    HPL_RETURN_LAST();
+}
+
+int64_t hpl_blur_gemm_f16_workspace(int64_t filter_size, int64_t c_in, int64_t c_out) {
+    const int64_t kb_per_tap = (c_in + TK - 1) / TK, n_tiles = (c_out + TN - 1) / TN;
+    return n_tiles * filter_size * kb_per_tap * 2 * kBHalf + 16;       // image + the weight absmax slot
+}
+
+int hpl_blur_gemm_f16(const float* in, int64_t ld_in, int64_t n_in_rows, const void* nbr, int idx64, int64_t filter_size,
+                      int64_t n_out_rows, int64_t c_in, int64_t c_out, const float* w, const float* bias, int act, float* out,
+                      int64_t ld_out, int out_channel_major, void* workspace, const uint32_t* in_amax, void* stream) {
+    HPL_CHECK_ARG(in && w && out && workspace && in_amax && c_in > 0 && c_out > 0 && filter_size > 0 && c_in % 4 == 0);
+    HPL_CHECK_ARG(ld_in % 4 == 0 && ld_in >= c_in && ((uintptr_t)in & 15) == 0 && ((uintptr_t)workspace & 15) == 0);
+    HPL_CHECK_ARG(((uintptr_t)w & 15) == 0);
+    HPL_CHECK_ARG(nbr != nullptr || filter_size == 1);
+    HPL_CHECK_ARG(out_channel_major ? ld_out >= n_out_rows : ld_out >= c_out);
+    if (n_out_rows == 0) return 0;
+    cudaStream_t s = as_stream(stream);
+    set_attrs();
+    const int kb_per_tap = (int)((c_in + TK - 1) / TK);
+    const long long n_tiles = (c_out + TN - 1) / TN;
+    const long long image_bytes = n_tiles * filter_size * kb_per_tap * 2 * kBHalf;
+    uint8_t* image = reinterpret_cast<uint8_t*>(workspace);
+    uint32_t* w_amax = reinterpret_cast<uint32_t*>(image + image_bytes);
+    const long long w_count = filter_size * c_in * c_out;
+    const int rc = hpl_absmax(w, w_count, w_amax, stream);
+    if (rc != 0) return rc;
+    const long long chunks = n_tiles * filter_size * kb_per_tap * (TN * (TK / 8));
+    weight_image16_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, s>>>(w, (int)filter_size, (int)c_in, (int)c_out, kb_per_tap, w_amax, image);
+    const long long steps = (long long)filter_size * kb_per_tap * (TK / 16);
+    const int n_main = steps <= 160 ? 1 : (steps <= 480 ? 3 : 7);
+    dim3 grid((unsigned)((n_out_rows + TM - 1) / TM), (unsigned)n_tiles);
+    if (idx64)
+        gather_gemm_f16_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, (int)c_in, (int)c_out,
+                                                                        kb_per_tap, image, bias, act, out, ld_out, out_channel_major, n_main, in_amax, w_amax);
+    else
+        gather_gemm_f16_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, (int)c_in, (int)c_out,
+                                                                         kb_per_tap, image, bias, act, out, ld_out, out_channel_major, n_main, in_amax, w_amax);
+    HPL_RETURN_LAST();
+}
+
+int hpl_blur_wgrad_f16(const float* in, int64_t ld_in, int64_t n_in_rows, const void* nbr, int idx64, int64_t filter_size,
+                       int64_t n_out_rows, int64_t c_in, int64_t c_out, const float* dz, int64_t ld_dz, float* dw, float* db,
+                       const uint32_t* in_amax, const uint32_t* dz_amax, void* stream) {
+    HPL_CHECK_ARG(in && dz && dw && in_amax && dz_amax && c_in > 0 && c_out > 0 && filter_size > 0 && c_in % 8 == 0);
+    HPL_CHECK_ARG(ld_in % 4 == 0 && ld_in >= c_in && ((uintptr_t)in & 15) == 0);
+    HPL_CHECK_ARG(ld_dz % 4 == 0 && ld_dz >= c_out && ((uintptr_t)dz & 15) == 0 && ((uintptr_t)dw & 15) == 0);
+    HPL_CHECK_ARG(nbr != nullptr || filter_size == 1);
+    if (n_out_rows == 0) return 0;
+    set_attrs();
+    const long long m_tiles = (filter_size * c_in + TM - 1) / TM, n_tiles = (c_out + TN - 1) / TN;
+    const long long base = m_tiles * n_tiles;
+    long long splits = (4LL * num_sms() + base - 1) / base;
+    const long long max_splits = (n_out_rows + 8 * TK - 1) / (8 * TK);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    long long rows_per_split = (n_out_rows + splits - 1) / splits;
+    rows_per_split = (rows_per_split + TK - 1) / TK * TK;
+    const long long max_rows = 160LL * WG_MAIN * 16;                       // <= ~160 accumulate steps (K = 16) per accumulator
+    if (rows_per_split > max_rows) rows_per_split = max_rows;
+    splits = (n_out_rows + rows_per_split - 1) / rows_per_split;
+    HPL_CHECK_ARG(m_tiles <= 65535 && n_tiles <= 65535);
+    dim3 grid((unsigned)splits, (unsigned)m_tiles, (unsigned)n_tiles);
+    cudaStream_t s = as_stream(stream);
+    if (idx64)
+        wgrad_f16_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, (int)c_in, (int)c_out, dz,
+                                                                  ld_dz, dw, rows_per_split, in_amax, dz_amax);
+    else
+        wgrad_f16_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, (int)c_in, (int)c_out, dz,
+                                                                   ld_dz, dw, rows_per_split, in_amax, dz_amax);
+    if (db != nullptr) return hpl_column_sums(dz, ld_dz, n_out_rows, c_out, db, stream);
+    HPL_RETURN_LAST();
+}
+
+}  // extern "C"

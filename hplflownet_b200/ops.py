@@ -10,10 +10,11 @@ from . import _lib
 
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 
-# Contraction engine: 1 = tcgen05 tensor cores with 3xTF32 compensation (default), 0 = fp32 FMA on
-# CUDA cores (parity anchor).  Both are hand-written sm_100a kernels; HPL_GEMM_PRECISION overrides.
+# Contraction engine: 2 = tcgen05 with a scaled FP16 hi/lo split ("3xFP16", half the operand bytes),
+# 1 = tcgen05 with 3xTF32 compensation, 0 = fp32 FMA on CUDA cores (parity anchor).  All are hand-written
+# sm_100a kernels with fp32-level accuracy; HPL_GEMM_PRECISION overrides the default.
 import os as _os
-DEFAULT_PRECISION = int(_os.environ.get("HPL_GEMM_PRECISION", "1"))
+DEFAULT_PRECISION = int(_os.environ.get("HPL_GEMM_PRECISION", "2"))
 _tc_workspace = {}
 
 
@@ -101,9 +102,17 @@ def reciprocal_(wsum):
     return wsum
 
 
+def absmax(t):
+    """Device scalar (int32 tensor holding fp32 bits) = max |t| over the whole buffer (pads are zero)."""
+    _f32(t, "t")
+    out = torch.empty(1, dtype=torch.int32, device=t.device)
+    _lib.call("hpl_absmax", t.data_ptr(), t.numel(), out.data_ptr(), _stream())
+    return out
+
+
 def tc_path(c_in, precision=None):
     """True when the tensor-core kernels (which can fold ``row_scale``) will run for this operand."""
-    return (DEFAULT_PRECISION if precision is None else precision) == 1 and c_in % 4 == 0
+    return (DEFAULT_PRECISION if precision is None else precision) >= 1 and c_in % 4 == 0
 
 
 def gather_rows(rows, channels, bary, off, scale=None, bias=None):
@@ -119,7 +128,7 @@ def gather_rows(rows, channels, bary, off, scale=None, bias=None):
 
 
 def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_major=False, precision=None,
-              tag="fwd", row_scale=None):
+              tag="fwd", row_scale=None, x_amax=None):
     """out[v] = act(bias + sum_f x[nbr[f, v]] @ w[f]);  w (F, C, Co)."""
     _f32(x, "x"); _f32(w, "w")
     f, c, co = w.shape
@@ -137,7 +146,19 @@ def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_majo
     if precision is None:
         precision = DEFAULT_PRECISION
     bias_ptr = bias.data_ptr() if bias is not None else None
-    if precision == 1:
+    if precision == 2 and (c % 4 != 0 or row_scale is not None):
+        precision = 1
+    if precision == 1 and c % 4 != 0:
+        precision = 0
+    if precision == 2:
+        ws = _workspace(x.device, _lib.load().hpl_blur_gemm_f16_workspace(f, c, co))
+        if x_amax is None:
+            x_amax = absmax(x)
+        with _timed(tag):
+            _lib.call("hpl_blur_gemm_f16", x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, f, n_out_rows, c, co,
+                      w.data_ptr(), bias_ptr, act, out.data_ptr(), out.stride(0), int(out_channel_major),
+                      ws.data_ptr(), x_amax.data_ptr(), _stream())
+    elif precision == 1:
         ws = _workspace(x.device, _lib.load().hpl_blur_gemm_tc_workspace(f, c, co))
         with _timed(tag):
             _lib.call("hpl_blur_gemm_tc", x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, f, n_out_rows, c, co,
@@ -152,7 +173,8 @@ def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_majo
     return out
 
 
-def blur_wgrad(x, c_in, nbr, n_out_rows, dz, c_out, filter_size, want_db=True, precision=None, row_scale=None):
+def blur_wgrad(x, c_in, nbr, n_out_rows, dz, c_out, filter_size, want_db=True, precision=None, row_scale=None,
+               x_amax=None, dz_amax=None):
     """Returns dw (F, C, Co), db (Co)."""
     _f32(x, "x"); _f32(dz, "dz")
     if nbr is not None:
@@ -164,7 +186,17 @@ def blur_wgrad(x, c_in, nbr, n_out_rows, dz, c_out, filter_size, want_db=True, p
     db = torch.zeros(c_out, dtype=torch.float32, device=x.device) if want_db else None
     if precision is None:
         precision = DEFAULT_PRECISION
-    tc = precision == 1 and c_in % 4 == 0
+    if precision == 2 and c_in % 8 == 0 and row_scale is None:
+        if x_amax is None:
+            x_amax = absmax(x)
+        if dz_amax is None:
+            dz_amax = absmax(dz)
+        with _timed("wgrad"):
+            _lib.call("hpl_blur_wgrad_f16", x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, filter_size,
+                      n_out_rows, c_in, c_out, dz.data_ptr(), dz.stride(0), dw.data_ptr(),
+                      db.data_ptr() if want_db else None, x_amax.data_ptr(), dz_amax.data_ptr(), _stream())
+        return dw, db
+    tc = precision >= 1 and c_in % 4 == 0
     assert tc or row_scale is None
     extra = (row_scale.data_ptr() if row_scale is not None else None,) if tc else ()
     fn = "hpl_blur_wgrad_tc" if tc else "hpl_blur_wgrad"

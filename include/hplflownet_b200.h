@@ -114,6 +114,25 @@ int hpl_blur_wgrad_tc(const float* in, int64_t ld_in, int64_t n_in_rows, const v
                       const float* dz, int64_t ld_dz, float* dw, float* db, const float* row_scale,
                       void* stream);
 
+/* "3xFP16" variants of the two tensor-core contractions (csrc/gemm_tc16.cu): same contracts and
+ * the same fp32-level accuracy as the 3xTF32 kernels, half the operand bytes through shared memory.
+ * Operands are split hi + lo*2^-11 in FP16 after scaling by a per-tensor power of two derived from
+ * max|x|, which the caller provides as a DEVICE scalar holding the fp32 bit pattern of max|x|:
+ *   hpl_absmax(x, count, out_bits)      out_bits <- bits(max_i |x[i]|), x 16-byte aligned
+ * (for a vertex-major matrix pass the whole (rows * ld) buffer; pad columns are zero).
+ * hpl_blur_gemm_f16: c_in % 4 == 0; workspace = hpl_blur_gemm_f16_workspace(F, C, Co) bytes.
+ * hpl_blur_wgrad_f16: c_in % 8 == 0. */
+int hpl_absmax(const float* x, int64_t count, uint32_t* out_bits, void* stream);
+int64_t hpl_blur_gemm_f16_workspace(int64_t filter_size, int64_t c_in, int64_t c_out);
+int hpl_blur_gemm_f16(const float* in, int64_t ld_in, int64_t n_in_rows, const void* nbr, int idx64,
+                      int64_t filter_size, int64_t n_out_rows, int64_t c_in, int64_t c_out,
+                      const float* w, const float* bias, int act, float* out, int64_t ld_out,
+                      int out_channel_major, void* workspace, const uint32_t* in_amax, void* stream);
+int hpl_blur_wgrad_f16(const float* in, int64_t ld_in, int64_t n_in_rows, const void* nbr, int idx64,
+                       int64_t filter_size, int64_t n_out_rows, int64_t c_in, int64_t c_out,
+                       const float* dz, int64_t ld_dz, float* dw, float* db, const uint32_t* in_amax,
+                       const uint32_t* dz_amax, void* stream);
+
 /* sums[c] += sum_v rows[v, c]  (conv bias gradients). rows (n_rows, ld) vertex-major. */
 int hpl_column_sums(const float* rows, int64_t ld, int64_t n_rows, int64_t channels, float* sums,
                     void* stream);

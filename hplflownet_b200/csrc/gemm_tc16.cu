@@ -15,6 +15,14 @@
 // TMEM accumulators and the main term is spread over 1/3/7 accumulators by K range (truncation bias, see
 // gemm_tc.cu).  Layouts: forward operands K-major no-swizzle, weight-gradient operands MN-major no-swizzle
 // (valid for 16-bit elements; address maps verified with tools/umma_probe.cu).
+//
+// Gather mapping (ncu-driven): a 128-bit LDG is serviced one quarter warp at a time, so the 8 lanes of a
+// quarter warp must read ONE 128-byte line (one wavefront) -- lanes are (row = lane / 8, 16-byte chunk =
+// lane % 8), i.e. 4 gathered rows x 128 contiguous bytes per warp instruction.  The first version had the 8
+// lanes of a quarter warp on 8 different rows: 32 wavefronts per instruction and the L1 data pipe at ~80 %.
+// Each lane then owns 4 consecutive K (or M) elements = half of a 16-byte operand chunk and stores hi / lo
+// with 8-byte STS; the chunk strides (LBO / SBO, free parameters of the UMMA descriptor) are padded by 32
+// bytes so that the 4 chunks a half warp touches fall into 4 different bank groups (conflict-free).
 #include <cuda_fp16.h>
 
 #include "tc_common.cuh"
@@ -29,11 +37,12 @@ constexpr int kStages = 4;
 constexpr int kProducerWarps = 8;
 constexpr int kThreads = kProducerWarps * 32 + 64;
 constexpr int kPrefetch = 2;                 // stages of gathered rows in flight per producer thread
-constexpr int kAHalf = TM * TK * 2;          // 8 KB
+constexpr uint32_t kA_LBO = TM * 16 + 32;    // K-chunk stride of the A tile, padded: 2080
+constexpr uint32_t kB_LBO = TN * 16, kSBO = 128;
+constexpr int kAHalf = (TK / 8) * kA_LBO;    // 8320 B: hi (or lo) part of the A stage
 constexpr int kBHalf = TN * TK * 2;          // 4 KB
 constexpr int kStageBytes = 2 * kAHalf + 2 * kBHalf;
 constexpr int kSmemBytes = kStages * kStageBytes + 1024;
-constexpr uint32_t kA_LBO = TM * 16, kB_LBO = TN * 16, kSBO = 128;
 constexpr uint32_t kIdescK = instr_desc(0, TM, TN, 0, 0);
 constexpr uint32_t kIdescMN = instr_desc(0, TM, TN, 1, 1);
 constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
@@ -45,6 +54,19 @@ __device__ __forceinline__ void scale_from_amax(uint32_t bits, float& scale, flo
     se = se < -100 ? -100 : (se > 100 ? 100 : se);
     scale = __uint_as_float((uint32_t)(se + 127) << 23);
     inv_scale = __uint_as_float((uint32_t)(127 - se) << 23);
+}
+
+// 4 consecutive fp32 -> 4 hi halves + 4 lo halves (2 x b32 each)
+__device__ __forceinline__ void split4h(const float4 a, float inv_s, uint32_t* hi, uint32_t* lo) {
+    const float x[4] = {a.x * inv_s, a.y * inv_s, a.z * inv_s, a.w * inv_s};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const __half2 h = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+        const float2 f = __half22float2(h);
+        const __half2 l = __floats2half2_rn((x[2 * i] - f.x) * kLoScale, (x[2 * i + 1] - f.y) * kLoScale);
+        hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+    }
 }
 
 // 8 consecutive fp32 -> 8 hi halves + 8 lo halves (4 x b32 each)
@@ -147,30 +169,35 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
     scale_from_amax(__ldg(w_amax), s_w, inv_w);
 
     if (warp < kProducerWarps) {
-        const int q = lane >> 3, r8 = lane & 7;          // 32-byte source granule (8 K elements) / row in group
-        int row[2] = {-1, -1};
-        float4 pre[kPrefetch][2][2];
+        // lane = (row within a group of 4, 16-byte chunk of a 128-byte line): one line per quarter warp
+        const int rq = lane >> 3, c16 = lane & 7;
+        int row[4] = {-1, -1, -1, -1};
+        float4 pre[kPrefetch][4];
+        uint32_t off[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int ml = warp * 16 + b * 4 + rq;                       // row of the tile
+            off[b] = (c16 >> 1) * kA_LBO + (ml >> 3) * 128 + (ml & 7) * 16 + (c16 & 1) * 8;
+        }
         auto load_rows = [&](int f) {
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const long long v = m0 + (warp * 2 + i) * 8 + r8;
+            for (int b = 0; b < 4; ++b) {
+                const long long v = m0 + warp * 16 + b * 4 + rq;
                 int r = -1;
                 if (v < n_out_rows) {
                     r = nbr != nullptr ? load_idx<I64>(nbr, (long long)f * n_out_rows + v) : (int)v;
                     if (r >= n_in_rows) r = -1;
                 }
-                row[i] = r;
+                row[b] = r;
             }
         };
-        auto issue = [&](int kb, float4 (*dst)[2]) {
-            const int f = kb / kb_per_tap, c = (kb - f * kb_per_tap) * TK + 8 * q;
+        auto issue = [&](int kb, float4* dst) {
+            const int f = kb / kb_per_tap, c = (kb - f * kb_per_tap) * TK + 4 * c16;
             if (kb % kb_per_tap == 0) load_rows(f);
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const float* p = in + (long long)row[i] * ld_in + c;
-                dst[i][0] = (row[i] >= 0 && c < c_in) ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                dst[i][1] = (row[i] >= 0 && c + 4 < c_in) ? __ldg(reinterpret_cast<const float4*>(p + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            for (int b = 0; b < 4; ++b)
+                dst[b] = (row[b] >= 0 && c < c_in) ? __ldg(reinterpret_cast<const float4*>(in + (long long)row[b] * ld_in + c))
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
         };
 #pragma unroll
         for (int d = 0; d < kPrefetch; ++d)
@@ -183,18 +210,17 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
                 if (kb >= n_kb) break;
                 const int stage = kb % kStages;
                 const uint32_t phase = (kb / kStages) & 1;
-                uint32_t hi[2][4], lo[2][4];
+                uint32_t hi[4][2], lo[4][2];
 #pragma unroll
-                for (int i = 0; i < 2; ++i) split8(pre[d][i][0], pre[d][i][1], inv_in, hi[i], lo[i]);
+                for (int b = 0; b < 4; ++b) split4h(pre[d][b], inv_in, hi[b], lo[b]);
                 if (kb + kPrefetch < n_kb) issue(kb + kPrefetch, pre[d]);
                 if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
                 __syncwarp();
                 const uint32_t a_hi = smem_base + stage * kStageBytes;
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const uint32_t off = q * (TM * 16) + (warp * 2 + i) * 128 + r8 * 16;
-                    sts128(a_hi + off, hi[i][0], hi[i][1], hi[i][2], hi[i][3]);
-                    sts128(a_hi + kAHalf + off, lo[i][0], lo[i][1], lo[i][2], lo[i][3]);
+                for (int b = 0; b < 4; ++b) {
+                    sts64(a_hi + off[b], hi[b][0], hi[b][1]);
+                    sts64(a_hi + kAHalf + off[b], lo[b][0], lo[b][1]);
                 }
                 fence_proxy_async();
                 __syncwarp();
@@ -296,8 +322,14 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
 // dw[(f,c), o] += sum_v in[nbr[f,v], c] * dz[v, o];  both operands MN-major no-swizzle fp16:
 //   element (m, k) at (k / 8) * LBO + (m / 8) * 128 + (k % 8) * 16 + (m % 8) * 2
 constexpr int WG_MAIN = 3;
-constexpr uint32_t kWA_LBO = (TM / 8) * 128;      // 2048: next 8 vertices of the A tile
-constexpr uint32_t kWB_LBO = (TN / 8) * 128;      // 1024
+constexpr int kWStages = 3;
+constexpr uint32_t kW_SBO = 128 + 32;                       // MN-chunk stride, padded (bank spreading)
+constexpr uint32_t kWA_LBO = (TM / 8) * kW_SBO;             // 2560: next 8 vertices of the A tile
+constexpr uint32_t kWB_LBO = (TN / 8) * kW_SBO;             // 1280
+constexpr int kWAHalf = (TK / 8) * kWA_LBO;                 // 10240
+constexpr int kWBHalf = (TK / 8) * kWB_LBO;                 // 5120
+constexpr int kWStageBytes = 2 * kWAHalf + 2 * kWBHalf;     // 30720
+constexpr int kWSmemBytes = kWStages * kWStageBytes + 1024;
 
 template <bool I64>
 __global__ void __launch_bounds__(kThreads, 2)
@@ -307,7 +339,7 @@ wgrad_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_r
                  const uint32_t* __restrict__ dz_amax) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], accum_bar;
+    __shared__ __align__(8) uint64_t full_bar[kWStages], empty_bar[kWStages], accum_bar;
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -319,7 +351,7 @@ wgrad_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_r
     const uint32_t tmem_cols = (uint32_t)(TN * (WG_MAIN + 1));
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < kWStages; ++s) {
             mbar_init(&full_bar[s], kProducerWarps);
             mbar_init(&empty_bar[s], 1);
         }
@@ -337,42 +369,51 @@ wgrad_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_r
     scale_from_amax(__ldg(dz_amax), s_dz, inv_dz);
 
     if (warp < kProducerWarps) {
-        const int q = lane >> 3, r8 = lane & 7;           // MN chunk inside the warp task / vertex inside the K group
-        int tap[2], ch[2], kk_a[2];
-        uint32_t off_a[2];
+        // lane = (vertex within a group of 4, 16-byte chunk of a 128-byte line): one line per quarter warp
+        const int rq = lane >> 3, c16 = lane & 7;
+        int tap[4], ch[4], kk_a[4];
+        uint32_t off_a[4];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int wt = warp * 2 + i;
-            const int kgrp = wt & 3, mc = (wt >> 2) * 4 + q;          // 4 K groups x 16 chunks of 8 rows of M
-            kk_a[i] = kgrp * 8 + r8;
-            const int m = m0 + mc * 8;
-            tap[i] = m < m_total ? m / c_in : -1;
-            ch[i] = m < m_total ? m - tap[i] * c_in : 0;
-            off_a[i] = kgrp * kWA_LBO + mc * 128 + r8 * 16;
+        for (int t = 0; t < 4; ++t) {                        // A: 4 segments of 32 M rows x 8 vertex quads
+            const int wt = warp * 4 + t;
+            const int seg = wt & 3, vq = wt >> 2;
+            kk_a[t] = vq * 4 + rq;
+            const int m = m0 + seg * 32 + 4 * c16;
+            tap[t] = m < m_total ? m / c_in : -1;
+            ch[t] = m < m_total ? m - tap[t] * c_in : 0;
+            off_a[t] = (vq >> 1) * kWA_LBO + (seg * 4 + (c16 >> 1)) * kW_SBO + ((vq & 1) * 4 + rq) * 16 + (c16 & 1) * 8;
         }
-        const int kgrp_b = warp & 3, nc = (warp >> 2) * 4 + q;        // 4 K groups x 8 chunks of N
-        const int kk_b = kgrp_b * 8 + r8, n_b = nc * 8;
-        const uint32_t off_b = kgrp_b * kWB_LBO + nc * 128 + r8 * 16;
+        int kk_b[2], n_b[2];
+        uint32_t off_b[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {                        // B: 2 segments of 32 outputs x 8 vertex quads
+            const int wt = warp * 2 + t;
+            const int seg = wt & 1, vq = wt >> 1;
+            kk_b[t] = vq * 4 + rq;
+            n_b[t] = seg * 32 + 4 * c16;
+            off_b[t] = (vq >> 1) * kWB_LBO + (seg * 4 + (c16 >> 1)) * kW_SBO + ((vq & 1) * 4 + rq) * 16 + (c16 & 1) * 8;
+        }
 
-        float4 pre[kPrefetch][3][2];
-        auto issue = [&](int kb, float4 (*dst)[2]) {
+        float4 pre[kPrefetch][6];
+        auto issue = [&](int kb, float4* dst) {
             const long long vb = v_lo + (long long)kb * TK;
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const long long v = vb + kk_a[i];
+            for (int t = 0; t < 4; ++t) {
+                const long long v = vb + kk_a[t];
                 int r = -1;
-                if (v < v_hi && tap[i] >= 0) {
-                    r = nbr != nullptr ? load_idx<I64>(nbr, (long long)tap[i] * n_out_rows + v) : (int)v;
+                if (v < v_hi && tap[t] >= 0) {
+                    r = nbr != nullptr ? load_idx<I64>(nbr, (long long)tap[t] * n_out_rows + v) : (int)v;
                     if (r >= n_in_rows) r = -1;
                 }
-                const float* p = in + (long long)r * ld_in + ch[i];
-                dst[i][0] = r >= 0 ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                dst[i][1] = r >= 0 ? __ldg(reinterpret_cast<const float4*>(p + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                dst[t] = r >= 0 ? __ldg(reinterpret_cast<const float4*>(in + (long long)r * ld_in + ch[t]))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            const long long v = vb + kk_b;
-            const float* pz = dz + v * ld_dz + o0 + n_b;
-            dst[2][0] = (v < v_hi && o0 + n_b < c_out) ? __ldg(reinterpret_cast<const float4*>(pz)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            dst[2][1] = (v < v_hi && o0 + n_b + 4 < c_out) ? __ldg(reinterpret_cast<const float4*>(pz + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const long long v = vb + kk_b[t];
+                dst[4 + t] = (v < v_hi && o0 + n_b[t] < c_out) ? __ldg(reinterpret_cast<const float4*>(dz + v * ld_dz + o0 + n_b[t]))
+                                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         };
 #pragma unroll
         for (int d = 0; d < kPrefetch; ++d)
@@ -383,23 +424,27 @@ wgrad_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_r
             for (int d = 0; d < kPrefetch; ++d) {
                 const int kb = kb0 + d;
                 if (kb >= n_kb) break;
-                const int stage = kb % kStages;
-                const uint32_t phase = (kb / kStages) & 1;
-                uint32_t hi[3][4], lo[3][4];
-                split8(pre[d][0][0], pre[d][0][1], inv_in, hi[0], lo[0]);
-                split8(pre[d][1][0], pre[d][1][1], inv_in, hi[1], lo[1]);
-                split8(pre[d][2][0], pre[d][2][1], inv_dz, hi[2], lo[2]);
+                const int stage = kb % kWStages;
+                const uint32_t phase = (kb / kWStages) & 1;
+                uint32_t hi[6][2], lo[6][2];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) split4h(pre[d][t], inv_in, hi[t], lo[t]);
+#pragma unroll
+                for (int t = 4; t < 6; ++t) split4h(pre[d][t], inv_dz, hi[t], lo[t]);
                 if (kb + kPrefetch < n_kb) issue(kb + kPrefetch, pre[d]);
                 if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
                 __syncwarp();
-                const uint32_t a_hi = smem_base + stage * kStageBytes;
+                const uint32_t a_hi = smem_base + stage * kWStageBytes;
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    sts128(a_hi + off_a[i], hi[i][0], hi[i][1], hi[i][2], hi[i][3]);
-                    sts128(a_hi + kAHalf + off_a[i], lo[i][0], lo[i][1], lo[i][2], lo[i][3]);
+                for (int t = 0; t < 4; ++t) {
+                    sts64(a_hi + off_a[t], hi[t][0], hi[t][1]);
+                    sts64(a_hi + kWAHalf + off_a[t], lo[t][0], lo[t][1]);
                 }
-                sts128(a_hi + 2 * kAHalf + off_b, hi[2][0], hi[2][1], hi[2][2], hi[2][3]);
-                sts128(a_hi + 2 * kAHalf + kBHalf + off_b, lo[2][0], lo[2][1], lo[2][2], lo[2][3]);
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    sts64(a_hi + 2 * kWAHalf + off_b[t], hi[4 + t][0], hi[4 + t][1]);
+                    sts64(a_hi + 2 * kWAHalf + kWBHalf + off_b[t], lo[4 + t][0], lo[4 + t][1]);
+                }
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full_bar[stage]);
@@ -409,19 +454,19 @@ wgrad_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_r
         if (lane == 0) {
             int last_g = -1;
             for (int kb = 0; kb < n_kb; ++kb) {
-                const int stage = kb % kStages;
+                const int stage = kb % kWStages;
                 const int g = (int)((long long)kb * WG_MAIN / n_kb);
                 const uint32_t tmem_main = tmem_d + (uint32_t)(TN * (1 + g));
-                mbar_wait(&full_bar[stage], (kb / kStages) & 1);
+                mbar_wait(&full_bar[stage], (kb / kWStages) & 1);
                 fence_after();
-                const uint32_t a_hi = smem_base + stage * kStageBytes;
-                const uint32_t a_lo = a_hi + kAHalf, b_hi = a_hi + 2 * kAHalf, b_lo = b_hi + kBHalf;
+                const uint32_t a_hi = smem_base + stage * kWStageBytes;
+                const uint32_t a_lo = a_hi + kWAHalf, b_hi = a_hi + 2 * kWAHalf, b_lo = b_hi + kWBHalf;
 #pragma unroll
                 for (int j = 0; j < TK / 16; ++j) {                      // one MMA = 2 K groups of 8 vertices
-                    const uint64_t dah = smem_desc(a_hi + j * 2 * kWA_LBO, kWA_LBO, kSBO);
-                    const uint64_t dal = smem_desc(a_lo + j * 2 * kWA_LBO, kWA_LBO, kSBO);
-                    const uint64_t dbh = smem_desc(b_hi + j * 2 * kWB_LBO, kWB_LBO, kSBO);
-                    const uint64_t dbl = smem_desc(b_lo + j * 2 * kWB_LBO, kWB_LBO, kSBO);
+                    const uint64_t dah = smem_desc(a_hi + j * 2 * kWA_LBO, kWA_LBO, kW_SBO);
+                    const uint64_t dal = smem_desc(a_lo + j * 2 * kWA_LBO, kWA_LBO, kW_SBO);
+                    const uint64_t dbh = smem_desc(b_hi + j * 2 * kWB_LBO, kWB_LBO, kW_SBO);
+                    const uint64_t dbl = smem_desc(b_lo + j * 2 * kWB_LBO, kWB_LBO, kW_SBO);
                     umma_f16(tmem_d, dal, dbh, kIdescMN, (kb | j) != 0);
                     umma_f16(tmem_d, dah, dbl, kIdescMN, 1);
                     umma_f16(tmem_main, dah, dbh, kIdescMN, g == last_g);
@@ -480,8 +525,8 @@ void set_attrs() {
     if (done) return;
     cudaFuncSetAttribute(gather_gemm_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     cudaFuncSetAttribute(gather_gemm_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    cudaFuncSetAttribute(wgrad_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    cudaFuncSetAttribute(wgrad_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaFuncSetAttribute(wgrad_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmemBytes);
+    cudaFuncSetAttribute(wgrad_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmemBytes);
     done = true;
 }
 
@@ -547,7 +592,7 @@ int hpl_blur_gemm_f16(const float* in, int64_t ld_in, int64_t n_in_rows, const v
 int hpl_blur_wgrad_f16(const float* in, int64_t ld_in, int64_t n_in_rows, const void* nbr, int idx64, int64_t filter_size,
                        int64_t n_out_rows, int64_t c_in, int64_t c_out, const float* dz, int64_t ld_dz, float* dw, float* db,
                        const uint32_t* in_amax, const uint32_t* dz_amax, void* stream) {
-    HPL_CHECK_ARG(in && dz && dw && in_amax && dz_amax && c_in > 0 && c_out > 0 && filter_size > 0 && c_in % 8 == 0);
+    HPL_CHECK_ARG(in && dz && dw && in_amax && dz_amax && c_in > 0 && c_out > 0 && filter_size > 0 && c_in % 4 == 0);
     HPL_CHECK_ARG(ld_in % 4 == 0 && ld_in >= c_in && ((uintptr_t)in & 15) == 0);
     HPL_CHECK_ARG(ld_dz % 4 == 0 && ld_dz >= c_out && ((uintptr_t)dz & 15) == 0 && ((uintptr_t)dw & 15) == 0);
     HPL_CHECK_ARG(nbr != nullptr || filter_size == 1);
@@ -568,10 +613,10 @@ int hpl_blur_wgrad_f16(const float* in, int64_t ld_in, int64_t n_in_rows, const 
     dim3 grid((unsigned)splits, (unsigned)m_tiles, (unsigned)n_tiles);
     cudaStream_t s = as_stream(stream);
     if (idx64)
-        wgrad_f16_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, (int)c_in, (int)c_out, dz,
+        wgrad_f16_kernel<true><<<grid, kThreads, kWSmemBytes, s>>>(in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, (int)c_in, (int)c_out, dz,
                                                                   ld_dz, dw, rows_per_split, in_amax, dz_amax);
     else
-        wgrad_f16_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, (int)c_in, (int)c_out, dz,
+        wgrad_f16_kernel<false><<<grid, kThreads, kWSmemBytes, s>>>(in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, (int)c_in, (int)c_out, dz,
                                                                    ld_dz, dw, rows_per_split, in_amax, dz_amax);
     if (db != nullptr) return hpl_column_sums(dz, ld_dz, n_out_rows, c_out, db, stream);
     HPL_RETURN_LAST();

@@ -186,7 +186,7 @@ def blur_wgrad(x, c_in, nbr, n_out_rows, dz, c_out, filter_size, want_db=True, p
     db = torch.zeros(c_out, dtype=torch.float32, device=x.device) if want_db else None
     if precision is None:
         precision = DEFAULT_PRECISION
-    if precision == 2 and c_in % 8 == 0 and row_scale is None:
+    if precision == 2 and c_in % 4 == 0 and row_scale is None:
         if x_amax is None:
             x_amax = absmax(x)
         if dz_amax is None:

@@ -121,7 +121,7 @@ int hpl_blur_wgrad_tc(const float* in, int64_t ld_in, int64_t n_in_rows, const v
  *   hpl_absmax(x, count, out_bits)      out_bits <- bits(max_i |x[i]|), x 16-byte aligned
  * (for a vertex-major matrix pass the whole (rows * ld) buffer; pad columns are zero).
  * hpl_blur_gemm_f16: c_in % 4 == 0; workspace = hpl_blur_gemm_f16_workspace(F, C, Co) bytes.
- * hpl_blur_wgrad_f16: c_in % 8 == 0. */
+ * hpl_blur_wgrad_f16: c_in % 4 == 0. */
 int hpl_absmax(const float* x, int64_t count, uint32_t* out_bits, void* stream);
 int64_t hpl_blur_gemm_f16_workspace(int64_t filter_size, int64_t c_in, int64_t c_out);
 int hpl_blur_gemm_f16(const float* in, int64_t ld_in, int64_t n_in_rows, const void* nbr, int idx64,

@@ -172,6 +172,7 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
         // lane = (row within a group of 4, 16-byte chunk of a 128-byte line): one line per quarter warp
         const int rq = lane >> 3, c16 = lane & 7;
         int row[4] = {-1, -1, -1, -1};
+        int row_next[4];                                               // indices of the next tap, loaded one tap early
         float4 pre[kPrefetch][4];
         uint32_t off[4];
 #pragma unroll
@@ -179,18 +180,21 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
             const int ml = warp * 16 + b * 4 + rq;                       // row of the tile
             off[b] = (c16 >> 1) * kA_LBO + (ml >> 3) * 128 + (ml & 7) * 16 + (c16 & 1) * 8;
         }
-        auto load_rows = [&](int f) {
+        auto fetch_rows = [&](int f) {                                 // issue the index loads of tap f (no use yet)
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 const long long v = m0 + warp * 16 + b * 4 + rq;
                 int r = -1;
-                if (v < n_out_rows) {
-                    r = nbr != nullptr ? load_idx<I64>(nbr, (long long)f * n_out_rows + v) : (int)v;
-                    if (r >= n_in_rows) r = -1;
-                }
-                row[b] = r;
+                if (v < n_out_rows && f < filter_size) r = nbr != nullptr ? load_idx<I64>(nbr, (long long)f * n_out_rows + v) : (int)v;
+                row_next[b] = r;
             }
         };
+        auto load_rows = [&](int f) {                                  // adopt tap f's indices, start fetching tap f+1
+#pragma unroll
+            for (int b = 0; b < 4; ++b) row[b] = row_next[b] < n_in_rows ? row_next[b] : -1;
+            fetch_rows(f + 1);
+        };
+        fetch_rows(0);
         auto issue = [&](int kb, float4* dst) {
             const int f = kb / kb_per_tap, c = (kb - f * kb_per_tap) * TK + 4 * c16;
             if (kb % kb_per_tap == 0) load_rows(f);
@@ -395,16 +399,28 @@ wgrad_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_r
         }
 
         float4 pre[kPrefetch][6];
-        auto issue = [&](int kb, float4* dst) {
+        int idx_next[4];                                               // gathered-row indices of the next stage to issue
+        auto fetch_idx = [&](int kb) {
             const long long vb = v_lo + (long long)kb * TK;
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 const long long v = vb + kk_a[t];
                 int r = -1;
-                if (v < v_hi && tap[t] >= 0) {
+                if (kb < n_kb && v < v_hi && tap[t] >= 0)
                     r = nbr != nullptr ? load_idx<I64>(nbr, (long long)tap[t] * n_out_rows + v) : (int)v;
-                    if (r >= n_in_rows) r = -1;
-                }
+                idx_next[t] = r;
+            }
+        };
+        fetch_idx(0);
+        auto issue = [&](int kb, float4* dst) {                        // called with kb = 0, 1, 2, ... in order
+            const long long vb = v_lo + (long long)kb * TK;
+            int rr[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) rr[t] = idx_next[t] < n_in_rows ? idx_next[t] : -1;
+            fetch_idx(kb + 1);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int r = rr[t];
                 dst[t] = r >= 0 ? __ldg(reinterpret_cast<const float4*>(in + (long long)r * ld_in + ch[t]))
                                 : make_float4(0.f, 0.f, 0.f, 0.f);
             }

@@ -171,7 +171,7 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
     if (warp < kProducerWarps) {
         // lane = (row within a group of 4, 16-byte chunk of a 128-byte line): one line per quarter warp
         const int rq = lane >> 3, c16 = lane & 7;
-        int row[4] = {-1, -1, -1, -1};
+        const float* rowp[4] = {nullptr, nullptr, nullptr, nullptr};   // gathered rows of the current tap (+ chunk offset)
         int row_next[4];                                               // indices of the next tap, loaded one tap early
         float4 pre[kPrefetch][4];
         uint32_t off[4];
@@ -180,44 +180,47 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
             const int ml = warp * 16 + b * 4 + rq;                       // row of the tile
             off[b] = (c16 >> 1) * kA_LBO + (ml >> 3) * 128 + (ml & 7) * 16 + (c16 & 1) * 8;
         }
+        const long long v_first = m0 + warp * 16 + rq;
         auto fetch_rows = [&](int f) {                                 // issue the index loads of tap f (no use yet)
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-                const long long v = m0 + warp * 16 + b * 4 + rq;
+                const long long v = v_first + b * 4;
                 int r = -1;
                 if (v < n_out_rows && f < filter_size) r = nbr != nullptr ? load_idx<I64>(nbr, (long long)f * n_out_rows + v) : (int)v;
                 row_next[b] = r;
             }
         };
-        auto load_rows = [&](int f) {                                  // adopt tap f's indices, start fetching tap f+1
-#pragma unroll
-            for (int b = 0; b < 4; ++b) row[b] = row_next[b] < n_in_rows ? row_next[b] : -1;
-            fetch_rows(f + 1);
-        };
+        int tap_i = 0, kt_i = 0, issued = 0;                           // issue-side position: tap, K block inside the tap
         fetch_rows(0);
-        auto issue = [&](int kb, float4* dst) {
-            const int f = kb / kb_per_tap, c = (kb - f * kb_per_tap) * TK + 4 * c16;
-            if (kb % kb_per_tap == 0) load_rows(f);
+        auto issue = [&](float4* dst) {
+            if (kt_i == 0) {                                           // adopt this tap's rows, start fetching the next tap's
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    rowp[b] = (row_next[b] >= 0 && row_next[b] < n_in_rows) ? in + (long long)row_next[b] * ld_in + 4 * c16 : nullptr;
+                fetch_rows(tap_i + 1);
+            }
+            const int c = kt_i * TK;
+            const bool live = c + 4 * c16 < c_in;
 #pragma unroll
             for (int b = 0; b < 4; ++b)
-                dst[b] = (row[b] >= 0 && c < c_in) ? __ldg(reinterpret_cast<const float4*>(in + (long long)row[b] * ld_in + c))
-                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                dst[b] = (rowp[b] != nullptr && live) ? __ldg(reinterpret_cast<const float4*>(rowp[b] + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            ++issued;
+            if (++kt_i == kb_per_tap) { kt_i = 0; ++tap_i; }
         };
 #pragma unroll
         for (int d = 0; d < kPrefetch; ++d)
-            if (d < n_kb) issue(d, pre[d]);
+            if (d < n_kb) issue(pre[d]);
 
+        int stage = 0;
+        uint32_t phase = 0;
         for (int kb0 = 0; kb0 < n_kb; kb0 += kPrefetch) {
 #pragma unroll
             for (int d = 0; d < kPrefetch; ++d) {
-                const int kb = kb0 + d;
-                if (kb >= n_kb) break;
-                const int stage = kb % kStages;
-                const uint32_t phase = (kb / kStages) & 1;
+                if (kb0 + d >= n_kb) break;
                 uint32_t hi[4][2], lo[4][2];
 #pragma unroll
                 for (int b = 0; b < 4; ++b) split4h(pre[d][b], inv_in, hi[b], lo[b]);
-                if (kb + kPrefetch < n_kb) issue(kb + kPrefetch, pre[d]);
+                if (issued < n_kb) issue(pre[d]);
                 if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
                 __syncwarp();
                 const uint32_t a_hi = smem_base + stage * kStageBytes;
@@ -229,6 +232,7 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full_bar[stage]);
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == kProducerWarps) {

@@ -379,95 +379,92 @@ wgrad_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_r
     if (warp < kProducerWarps) {
         // lane = (vertex within a group of 4, 16-byte chunk of a 128-byte line): one line per quarter warp
         const int rq = lane >> 3, c16 = lane & 7;
-        int tap[4], ch[4], kk_a[4];
-        uint32_t off_a[4];
+        // Warp w owns vertex quad w of the stage (vertices 4w..4w+3); its 4 A tasks are the 4 segments of 32 M rows,
+        // its 2 B tasks the 2 segments of 32 outputs -> one vertex offset and one smem base per operand.
+        const int kk = warp * 4 + rq;                                  // vertex inside the stage
+        const uint32_t sm_row = (warp >> 1) * 1u, sm_in = ((warp & 1) * 4 + rq) * 16 + (c16 & 1) * 8;
+        const uint32_t base_a = sm_row * kWA_LBO + (c16 >> 1) * kW_SBO + sm_in;     // + seg * 4 * kW_SBO
+        const uint32_t base_b = sm_row * kWB_LBO + (c16 >> 1) * kW_SBO + sm_in;
+        int ch[4];                                                     // channel of this lane's chunk per segment, -1 = beyond M
+        unsigned ipos[4];                                              // element offset into nbr + v_lo (32-bit; host checks the range)
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {                        // A: 4 segments of 32 M rows x 8 vertex quads
-            const int wt = warp * 4 + t;
-            const int seg = wt & 3, vq = wt >> 2;
-            kk_a[t] = vq * 4 + rq;
-            const int m = m0 + seg * 32 + 4 * c16;
-            tap[t] = m < m_total ? m / c_in : -1;
-            ch[t] = m < m_total ? m - tap[t] * c_in : 0;
-            off_a[t] = (vq >> 1) * kWA_LBO + (seg * 4 + (c16 >> 1)) * kW_SBO + ((vq & 1) * 4 + rq) * 16 + (c16 & 1) * 8;
+        for (int t = 0; t < 4; ++t) {
+            const int m = m0 + t * 32 + 4 * c16;
+            const int tp = m < m_total ? m / c_in : -1;
+            ch[t] = tp >= 0 ? m - tp * c_in : -1;
+            ipos[t] = (unsigned)((nbr != nullptr && tp >= 0 ? (long long)tp * n_out_rows : 0) + kk);
         }
-        int kk_b[2], n_b[2];
-        uint32_t off_b[2];
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {                        // B: 2 segments of 32 outputs x 8 vertex quads
-            const int wt = warp * 2 + t;
-            const int seg = wt & 1, vq = wt >> 1;
-            kk_b[t] = vq * 4 + rq;
-            n_b[t] = seg * 32 + 4 * c16;
-            off_b[t] = (vq >> 1) * kWB_LBO + (seg * 4 + (c16 >> 1)) * kW_SBO + ((vq & 1) * 4 + rq) * 16 + (c16 & 1) * 8;
-        }
+        unsigned zpos = (unsigned)(kk * ld_dz + o0 + 4 * c16);          // element offset into dz + v_lo * ld_dz; segment t adds 32
+        const bool b_ok0 = o0 + 4 * c16 < c_out, b_ok1 = o0 + 32 + 4 * c16 < c_out;
+        const float* dz_base = dz + v_lo * ld_dz;
 
         float4 pre[kPrefetch][6];
         int idx_next[4];                                               // gathered-row indices of the next stage to issue
-        auto fetch_idx = [&](int kb) {
-            const long long vb = v_lo + (long long)kb * TK;
+        const int span = (int)(v_hi - v_lo);                           // vertices of this CTA
+        int fetched = 0, issued = 0;                                   // stages whose indices / data have been requested
+        auto fetch_idx = [&]() {
+            const int base = fetched * TK;
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                const long long v = vb + kk_a[t];
                 int r = -1;
-                if (kb < n_kb && v < v_hi && tap[t] >= 0)
-                    r = nbr != nullptr ? load_idx<I64>(nbr, (long long)tap[t] * n_out_rows + v) : (int)v;
+                if (base + kk < span && ch[t] >= 0)
+                    r = nbr != nullptr ? load_idx<I64>(nbr, v_lo + ipos[t]) : (int)(v_lo + ipos[t]);
                 idx_next[t] = r;
+                ipos[t] += TK;
             }
+            ++fetched;
         };
-        fetch_idx(0);
-        auto issue = [&](int kb, float4* dst) {                        // called with kb = 0, 1, 2, ... in order
-            const long long vb = v_lo + (long long)kb * TK;
+        fetch_idx();
+        auto issue = [&](float4* dst) {
+            const int base = issued * TK;
             int rr[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) rr[t] = idx_next[t] < n_in_rows ? idx_next[t] : -1;
-            fetch_idx(kb + 1);
+            fetch_idx();
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int r = rr[t];
-                dst[t] = r >= 0 ? __ldg(reinterpret_cast<const float4*>(in + (long long)r * ld_in + ch[t]))
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                const long long v = vb + kk_b[t];
-                dst[4 + t] = (v < v_hi && o0 + n_b[t] < c_out) ? __ldg(reinterpret_cast<const float4*>(dz + v * ld_dz + o0 + n_b[t]))
-                                                               : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            for (int t = 0; t < 4; ++t)
+                dst[t] = rr[t] >= 0 ? __ldg(reinterpret_cast<const float4*>(in + (long long)rr[t] * ld_in + ch[t]))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool v_ok = base + kk < span;
+            dst[4] = (v_ok && b_ok0) ? __ldg(reinterpret_cast<const float4*>(dz_base + zpos)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            dst[5] = (v_ok && b_ok1) ? __ldg(reinterpret_cast<const float4*>(dz_base + zpos + 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            zpos += (unsigned)(TK * ld_dz);
+            ++issued;
         };
 #pragma unroll
         for (int d = 0; d < kPrefetch; ++d)
-            if (d < n_kb) issue(d, pre[d]);
+            if (d < n_kb) issue(pre[d]);
 
+        int stage = 0;
+        uint32_t phase = 0;
         for (int kb0 = 0; kb0 < n_kb; kb0 += kPrefetch) {
 #pragma unroll
             for (int d = 0; d < kPrefetch; ++d) {
-                const int kb = kb0 + d;
-                if (kb >= n_kb) break;
-                const int stage = kb % kWStages;
-                const uint32_t phase = (kb / kWStages) & 1;
-                uint32_t hi[6][2], lo[6][2];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) split4h(pre[d][t], inv_in, hi[t], lo[t]);
-#pragma unroll
-                for (int t = 4; t < 6; ++t) split4h(pre[d][t], inv_dz, hi[t], lo[t]);
-                if (kb + kPrefetch < n_kb) issue(kb + kPrefetch, pre[d]);
+                if (kb0 + d >= n_kb) break;
                 if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
                 __syncwarp();
                 const uint32_t a_hi = smem_base + stage * kWStageBytes;
+                // convert and store one chunk at a time (keeps the live registers low: this kernel holds
+                // 12 gathered float4 per thread), then refill the slot with the loads of a later stage
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
-                    sts64(a_hi + off_a[t], hi[t][0], hi[t][1]);
-                    sts64(a_hi + kWAHalf + off_a[t], lo[t][0], lo[t][1]);
+                    uint32_t hi[2], lo[2];
+                    split4h(pre[d][t], inv_in, hi, lo);
+                    sts64(a_hi + base_a + t * 4 * kW_SBO, hi[0], hi[1]);
+                    sts64(a_hi + kWAHalf + base_a + t * 4 * kW_SBO, lo[0], lo[1]);
                 }
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
-                    sts64(a_hi + 2 * kWAHalf + off_b[t], hi[4 + t][0], hi[4 + t][1]);
-                    sts64(a_hi + 2 * kWAHalf + kWBHalf + off_b[t], lo[4 + t][0], lo[4 + t][1]);
+                    uint32_t hi[2], lo[2];
+                    split4h(pre[d][4 + t], inv_dz, hi, lo);
+                    sts64(a_hi + 2 * kWAHalf + base_b + t * 4 * kW_SBO, hi[0], hi[1]);
+                    sts64(a_hi + 2 * kWAHalf + kWBHalf + base_b + t * 4 * kW_SBO, lo[0], lo[1]);
                 }
+                if (issued < n_kb) issue(pre[d]);
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full_bar[stage]);
+                if (++stage == kWStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == kProducerWarps) {
@@ -630,6 +627,7 @@ int hpl_blur_wgrad_f16(const float* in, int64_t ld_in, int64_t n_in_rows, const 
     if (rows_per_split > max_rows) rows_per_split = max_rows;
     splits = (n_out_rows + rows_per_split - 1) / rows_per_split;
     HPL_CHECK_ARG(m_tiles <= 65535 && n_tiles <= 65535);
+    HPL_CHECK_ARG(filter_size * n_out_rows < (1LL << 31) && (rows_per_split + TK) * ld_dz < (1LL << 31));   // 32-bit in-kernel offsets
     dim3 grid((unsigned)splits, (unsigned)m_tiles, (unsigned)n_tiles);
     cudaStream_t s = as_stream(stream);
     if (idx64)

@@ -36,7 +36,8 @@ constexpr int TK = 32;                       // K elements per stage = 2 MMAs of
 constexpr int kStages = 4;
 constexpr int kProducerWarps = 8;
 constexpr int kThreads = kProducerWarps * 32 + 64;
-constexpr int kPrefetch = 2;                 // stages of gathered rows in flight per producer thread
+constexpr int kPrefetch = 2;                 // stages of gathered rows in flight per producer thread (weight gradient)
+constexpr int kPrefetchF = 3;                // ... forward / data-gradient kernel (4 float4 per stage)
 constexpr uint32_t kA_LBO = TM * 16 + 32;    // K-chunk stride of the A tile, padded: 2080
 constexpr uint32_t kB_LBO = TN * 16, kSBO = 128;
 constexpr int kAHalf = (TK / 8) * kA_LBO;    // 8320 B: hi (or lo) part of the A stage
@@ -164,6 +165,8 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
     fence_after();
     const uint32_t tmem_d = tmem_slot;
     const uint32_t smem_base = smem_u32(smem);
+    const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar), accum_a = smem_u32(&accum_bar);
+    const bool lane0 = lane == 0;
     float s_in, inv_in, s_w, inv_w;
     scale_from_amax(__ldg(in_amax), s_in, inv_in);
     scale_from_amax(__ldg(w_amax), s_w, inv_w);
@@ -173,7 +176,7 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
         const int rq = lane >> 3, c16 = lane & 7;
         const float* rowp[4] = {nullptr, nullptr, nullptr, nullptr};   // gathered rows of the current tap (+ chunk offset)
         int row_next[4];                                               // indices of the next tap, loaded one tap early
-        float4 pre[kPrefetch][4];
+        float4 pre[kPrefetchF][4];
         uint32_t off[4];
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
@@ -208,41 +211,40 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
             if (++kt_i == kb_per_tap) { kt_i = 0; ++tap_i; }
         };
 #pragma unroll
-        for (int d = 0; d < kPrefetch; ++d)
+        for (int d = 0; d < kPrefetchF; ++d)
             if (d < n_kb) issue(pre[d]);
 
         int stage = 0;
         uint32_t phase = 0;
-        for (int kb0 = 0; kb0 < n_kb; kb0 += kPrefetch) {
+        for (int kb0 = 0; kb0 < n_kb; kb0 += kPrefetchF) {
 #pragma unroll
-            for (int d = 0; d < kPrefetch; ++d) {
+            for (int d = 0; d < kPrefetchF; ++d) {
                 if (kb0 + d >= n_kb) break;
-                uint32_t hi[4][2], lo[4][2];
-#pragma unroll
-                for (int b = 0; b < 4; ++b) split4h(pre[d][b], inv_in, hi[b], lo[b]);
-                if (issued < n_kb) issue(pre[d]);
-                if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (lane0) mbar_wait_a(empty_a + 8 * stage, phase ^ 1);
                 __syncwarp();
                 const uint32_t a_hi = smem_base + stage * kStageBytes;
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    sts64(a_hi + off[b], hi[b][0], hi[b][1]);
-                    sts64(a_hi + kAHalf + off[b], lo[b][0], lo[b][1]);
+                for (int b = 0; b < 4; ++b) {                          // convert + store one chunk at a time (few live registers)
+                    uint32_t hi[2], lo[2];
+                    split4h(pre[d][b], inv_in, hi, lo);
+                    sts64(a_hi + off[b], hi[0], hi[1]);
+                    sts64(a_hi + kAHalf + off[b], lo[0], lo[1]);
                 }
+                if (issued < n_kb) issue(pre[d]);                      // refill the slot: 3 stages of loads stay in flight
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&full_bar[stage]);
+                if (lane0) mbar_arrive_a(full_a + 8 * stage);
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == kProducerWarps) {
         if (lane == 0) {
-            int last_g = -1;
+            int last_g = -1, stage = 0;
+            uint32_t phase = 0;
             for (int kb = 0; kb < n_kb; ++kb) {
-                const int stage = kb % kStages;
                 const int g = (int)((long long)kb * n_main / n_kb);
                 const uint32_t tmem_main = tmem_d + (uint32_t)(TN * (1 + g));
-                mbar_wait(&full_bar[stage], (kb / kStages) & 1);
+                mbar_wait_a(full_a + 8 * stage, phase);
                 fence_after();
                 const uint32_t a_hi = smem_base + stage * kStageBytes;
                 const uint32_t a_lo = a_hi + kAHalf, b_hi = a_hi + 2 * kAHalf, b_lo = b_hi + kBHalf;
@@ -257,24 +259,28 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
                     umma_f16(tmem_main, dah, dbh, kIdescK, g == last_g);
                     last_g = g;
                 }
-                umma_commit(&empty_bar[stage]);
+                umma_commit_a(empty_a + 8 * stage);
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&accum_bar);
+            umma_commit_a(accum_a);
         }
     } else {
         if (lane == 0) {
             const uint8_t* src = w_image + (long long)n_tile * n_kb * (2 * kBHalf);
+            int stage = 0;
+            uint32_t phase = 0;
             for (int kb = 0; kb < n_kb; ++kb) {
-                const int stage = kb % kStages;
-                mbar_wait(&empty_bar[stage], ((kb / kStages) & 1) ^ 1);
-                mbar_arrive_expect_tx(&full_bar[stage], 2 * kBHalf);
-                bulk_load(smem_base + stage * kStageBytes + 2 * kAHalf, src + (long long)kb * (2 * kBHalf), 2 * kBHalf, &full_bar[stage]);
+                mbar_wait_a(empty_a + 8 * stage, phase ^ 1);
+                mbar_arrive_expect_tx_a(full_a + 8 * stage, 2 * kBHalf);
+                bulk_load_a(smem_base + stage * kStageBytes + 2 * kAHalf, src, 2 * kBHalf, full_a + 8 * stage);
+                src += 2 * kBHalf;
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
     }
 
     if (warp < 4) {
-        mbar_wait(&accum_bar, 0);
+        mbar_wait_a(accum_a, 0);
         fence_after();
         const long long m = m0 + warp * 32 + lane;
         const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
@@ -372,6 +378,8 @@ wgrad_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_r
     fence_after();
     const uint32_t tmem_d = tmem_slot;
     const uint32_t smem_base = smem_u32(smem);
+    const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar), accum_a = smem_u32(&accum_bar);
+    const bool lane0 = lane == 0;
     float s_in, inv_in, s_dz, inv_dz;
     scale_from_amax(__ldg(in_amax), s_in, inv_in);
     scale_from_amax(__ldg(dz_amax), s_dz, inv_dz);
@@ -441,7 +449,7 @@ wgrad_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_r
 #pragma unroll
             for (int d = 0; d < kPrefetch; ++d) {
                 if (kb0 + d >= n_kb) break;
-                if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (lane0) mbar_wait_a(empty_a + 8 * stage, phase ^ 1);
                 __syncwarp();
                 const uint32_t a_hi = smem_base + stage * kWStageBytes;
                 // convert and store one chunk at a time (keeps the live registers low: this kernel holds
@@ -463,18 +471,18 @@ wgrad_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_r
                 if (issued < n_kb) issue(pre[d]);
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&full_bar[stage]);
+                if (lane0) mbar_arrive_a(full_a + 8 * stage);
                 if (++stage == kWStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == kProducerWarps) {
         if (lane == 0) {
-            int last_g = -1;
+            int last_g = -1, stage = 0;
+            uint32_t phase = 0;
             for (int kb = 0; kb < n_kb; ++kb) {
-                const int stage = kb % kWStages;
                 const int g = (int)((long long)kb * WG_MAIN / n_kb);
                 const uint32_t tmem_main = tmem_d + (uint32_t)(TN * (1 + g));
-                mbar_wait(&full_bar[stage], (kb / kWStages) & 1);
+                mbar_wait_a(full_a + 8 * stage, phase);
                 fence_after();
                 const uint32_t a_hi = smem_base + stage * kWStageBytes;
                 const uint32_t a_lo = a_hi + kWAHalf, b_hi = a_hi + 2 * kWAHalf, b_lo = b_hi + kWBHalf;
@@ -489,14 +497,15 @@ wgrad_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_r
                     umma_f16(tmem_main, dah, dbh, kIdescMN, g == last_g);
                     last_g = g;
                 }
-                umma_commit(&empty_bar[stage]);
+                umma_commit_a(empty_a + 8 * stage);
+                if (++stage == kWStages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&accum_bar);
+            umma_commit_a(accum_a);
         }
     }
 
     if (warp < 4 && n_kb > 0) {
-        mbar_wait(&accum_bar, 0);
+        mbar_wait_a(accum_a, 0);
         fence_after();
         const int m = m0 + warp * 32 + lane;
         const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);

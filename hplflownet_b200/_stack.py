@@ -17,10 +17,12 @@ def forward(x, c_in, n_rows, layers, first_nbr=None, last_channel_major=False, f
         last = l == len(layers) - 1
         direct_cm = last and last_channel_major and act == ops.ACT_NONE
         scale = first_row_scale if l == 0 else None
-        amax = ops.absmax(xs[-1]) if (ops.DEFAULT_PRECISION == 2 and scale is None) else None
-        amaxs.append(amax)
+        split = ops.DEFAULT_PRECISION >= 2 and scale is None and chans[-1] % 4 == 0
+        amax = ops.absmax(xs[-1]) if split else None
+        x16 = ops.split16(xs[-1], chans[-1], amax) if (split and ops.DEFAULT_PRECISION == 3) else None
+        amaxs.append((amax, x16))
         y = ops.blur_gemm(xs[-1], chans[-1], first_nbr if l == 0 else None, n_rows, w, b,
-                          act, out_channel_major=direct_cm, row_scale=scale, x_amax=amax)
+                          act, out_channel_major=direct_cm, row_scale=scale, x_amax=amax, x16=x16)
         if direct_cm:
             out_cm = y
         else:
@@ -41,16 +43,19 @@ def backward(dx, xs, chans, layers, n_rows, first_nbr, first_nbr_t, need_input_g
         if act != ops.ACT_NONE:
             ops.act_backward_(dx, xs[l + 1], chans[l + 1], act)
         tbl = first_nbr if l == 0 else None
-        dz_amax = ops.absmax(dx) if ops.DEFAULT_PRECISION == 2 else None      # shared by wgrad and dgrad
+        split = ops.DEFAULT_PRECISION >= 2 and chans[l + 1] % 4 == 0
+        dz_amax = ops.absmax(dx) if split else None                          # shared by wgrad and dgrad
+        dz16 = ops.split16(dx, chans[l + 1], dz_amax) if (split and ops.DEFAULT_PRECISION == 3) else None
+        x_amax, x16 = amaxs[l] if amaxs else (None, None)
         if need_param_grad[l]:
             grads[l] = ops.blur_wgrad(xs[l], chans[l], tbl, n_rows, dx, chans[l + 1], w.size(0), want_db=b is not None,
                                       row_scale=first_row_scale if l == 0 else None,
-                                      x_amax=amaxs[l] if amaxs else None, dz_amax=dz_amax)
+                                      x_amax=x_amax, dz_amax=dz_amax, x16=x16, dz16=dz16)
         if l > 0 or need_input_grad:
             wd = w.transpose(1, 2).contiguous()                       # (F, Co, C)
             tbl_t = first_nbr_t() if (l == 0 and first_nbr is not None) else None
             n_in = xs[l].size(0)
-            dx = ops.blur_gemm(dx, chans[l + 1], tbl_t, n_in, wd, None, ops.ACT_NONE, tag="dgrad", x_amax=dz_amax)
+            dx = ops.blur_gemm(dx, chans[l + 1], tbl_t, n_in, wd, None, ops.ACT_NONE, tag="dgrad", x_amax=dz_amax, x16=dz16)
         else:
             dx = None
     return dx, grads

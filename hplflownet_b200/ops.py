@@ -10,7 +10,9 @@ from . import _lib
 
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 
-# Contraction engine: 2 = tcgen05 with a scaled FP16 hi/lo split ("3xFP16", half the operand bytes),
+# Contraction engine: 2 = tcgen05 with a scaled FP16 hi/lo split done in registers per tap ("3xFP16", half
+# the operand bytes; default), 3 = same math with operands pre-split once in HBM and copied by cp.async
+# (parity-green, currently slower -- see csrc/gemm_tc16p.cu),
 # 1 = tcgen05 with 3xTF32 compensation, 0 = fp32 FMA on CUDA cores (parity anchor).  All are hand-written
 # sm_100a kernels with fp32-level accuracy; HPL_GEMM_PRECISION overrides the default.
 import os as _os
@@ -110,6 +112,15 @@ def absmax(t):
     return out
 
 
+def split16(x, channels, amax):
+    """fp16 hi/lo image of a vertex-major matrix (see include/hplflownet_b200.h: hpl_split16)."""
+    _f32(x, "x")
+    n = x.size(0)
+    buf = torch.empty(_lib.load().hpl_split16_bytes(n, channels), dtype=torch.uint8, device=x.device)
+    _lib.call("hpl_split16", x.data_ptr(), x.stride(0), n, channels, amax.data_ptr(), buf.data_ptr(), _stream())
+    return buf
+
+
 def tc_path(c_in, precision=None):
     """True when the tensor-core kernels (which can fold ``row_scale``) will run for this operand."""
     return (DEFAULT_PRECISION if precision is None else precision) >= 1 and c_in % 4 == 0
@@ -128,7 +139,7 @@ def gather_rows(rows, channels, bary, off, scale=None, bias=None):
 
 
 def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_major=False, precision=None,
-              tag="fwd", row_scale=None, x_amax=None):
+              tag="fwd", row_scale=None, x_amax=None, x16=None):
     """out[v] = act(bias + sum_f x[nbr[f, v]] @ w[f]);  w (F, C, Co)."""
     _f32(x, "x"); _f32(w, "w")
     f, c, co = w.shape
@@ -146,11 +157,22 @@ def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_majo
     if precision is None:
         precision = DEFAULT_PRECISION
     bias_ptr = bias.data_ptr() if bias is not None else None
+    if precision == 3 and (c % 4 != 0 or row_scale is not None):
+        precision = 1
     if precision == 2 and (c % 4 != 0 or row_scale is not None):
         precision = 1
     if precision == 1 and c % 4 != 0:
         precision = 0
-    if precision == 2:
+    if precision == 3:
+        ws = _workspace(x.device, _lib.load().hpl_blur_gemm_f16_workspace(f, c, co))
+        if x16 is None:
+            x_amax = absmax(x)
+            x16 = split16(x, c, x_amax)
+        with _timed(tag):
+            _lib.call("hpl_blur_gemm_p16", x16.data_ptr(), x.size(0), nbr_ptr, i64, f, n_out_rows, c, co,
+                      w.data_ptr(), bias_ptr, act, out.data_ptr(), out.stride(0), int(out_channel_major),
+                      ws.data_ptr(), x_amax.data_ptr(), _stream())
+    elif precision == 2:
         ws = _workspace(x.device, _lib.load().hpl_blur_gemm_f16_workspace(f, c, co))
         if x_amax is None:
             x_amax = absmax(x)
@@ -174,7 +196,7 @@ def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_majo
 
 
 def blur_wgrad(x, c_in, nbr, n_out_rows, dz, c_out, filter_size, want_db=True, precision=None, row_scale=None,
-               x_amax=None, dz_amax=None):
+               x_amax=None, dz_amax=None, x16=None, dz16=None):
     """Returns dw (F, C, Co), db (Co)."""
     _f32(x, "x"); _f32(dz, "dz")
     if nbr is not None:
@@ -186,6 +208,21 @@ def blur_wgrad(x, c_in, nbr, n_out_rows, dz, c_out, filter_size, want_db=True, p
     db = torch.zeros(c_out, dtype=torch.float32, device=x.device) if want_db else None
     if precision is None:
         precision = DEFAULT_PRECISION
+    if precision == 3 and c_in % 32 == 0 and row_scale is None:
+        if x16 is None:
+            x_amax = absmax(x)
+            x16 = split16(x, c_in, x_amax)
+        if dz16 is None:
+            dz_amax = absmax(dz)
+            dz16 = split16(dz, c_out, dz_amax)
+        with _timed("wgrad"):
+            _lib.call("hpl_blur_wgrad_p16", x16.data_ptr(), x.size(0), nbr_ptr, i64, filter_size, n_out_rows, c_in, c_out,
+                      dz16.data_ptr(), dw.data_ptr(), x_amax.data_ptr(), dz_amax.data_ptr(), _stream())
+            if want_db:
+                _lib.call("hpl_column_sums", dz.data_ptr(), dz.stride(0), n_out_rows, c_out, db.data_ptr(), _stream())
+        return dw, db
+    if precision == 3:
+        precision = 2
     if precision == 2 and c_in % 4 == 0 and row_scale is None:
         if x_amax is None:
             x_amax = absmax(x)

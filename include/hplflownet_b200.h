@@ -133,6 +133,26 @@ int hpl_blur_wgrad_f16(const float* in, int64_t ld_in, int64_t n_in_rows, const 
                        const float* dz, int64_t ld_dz, float* dw, float* db, const uint32_t* in_amax,
                        const uint32_t* dz_amax, void* stream);
 
+/* "Split once, copy many" variants (csrc/gemm_tc16p.cu): the operands of the 3xFP16 contractions are
+ * pre-split in HBM so the kernels only copy (cp.async) instead of re-splitting every element per tap.
+ *   hpl_split16(x, ld, n_rows, C, amax, x16): x16 = n_rows * ceil(C/32) lines of 128 bytes,
+ *     line = [32 hi halves | 32 lo halves] of one 32-channel block; hpl_split16_bytes gives the size;
+ *     x16 must be 128-byte aligned.
+ *   hpl_blur_gemm_p16 / hpl_blur_wgrad_p16: same contracts as the _f16 entry points with `in` (and `dz`)
+ *     replaced by their split images.  wgrad requires c_in % 32 == 0.  The forward workspace is
+ *     hpl_blur_gemm_f16_workspace(F, C, Co) bytes. */
+int64_t hpl_split16_bytes(int64_t n_rows, int64_t channels);
+int hpl_split16(const float* x, int64_t ld, int64_t n_rows, int64_t channels, const uint32_t* amax,
+                void* x16, void* stream);
+int hpl_blur_gemm_p16(const void* in16, int64_t n_in_rows, const void* nbr, int idx64,
+                      int64_t filter_size, int64_t n_out_rows, int64_t c_in, int64_t c_out,
+                      const float* w, const float* bias, int act, float* out, int64_t ld_out,
+                      int out_channel_major, void* workspace, const uint32_t* in_amax, void* stream);
+int hpl_blur_wgrad_p16(const void* in16, int64_t n_in_rows, const void* nbr, int idx64,
+                       int64_t filter_size, int64_t n_out_rows, int64_t c_in, int64_t c_out,
+                       const void* dz16, float* dw, const uint32_t* in_amax, const uint32_t* dz_amax,
+                       void* stream);
+
 /* sums[c] += sum_v rows[v, c]  (conv bias gradients). rows (n_rows, ld) vertex-major. */
 int hpl_column_sums(const float* rows, int64_t ld, int64_t n_rows, int64_t channels, float* sums,
                     void* stream);

@@ -27,7 +27,7 @@ def _reference(x, nbr, w, bias, act):
     return y
 
 
-@pytest.mark.parametrize("precision", [2, 1, 0])
+@pytest.mark.parametrize("precision", [3, 2, 1, 0])
 @pytest.mark.parametrize("h,c,co,f,act,cm", [
     (7599, 64, 64, 15, ops.ACT_NONE, False),     # cfg2 blur layer
     (1000, 68, 64, 15, ops.ACT_LEAKY, False),    # bcn1: K per tap not a multiple of 16
@@ -51,7 +51,7 @@ def test_gather_gemm_matches_float64(precision, h, c, co, f, act, cm):
     assert_close(got, _reference(x, nbr, w, bias, act), "gather-gemm precision=%d" % precision)
 
 
-@pytest.mark.parametrize("precision", [2, 1, 0])
+@pytest.mark.parametrize("precision", [3, 2, 1, 0])
 @pytest.mark.parametrize("h,c,co,f", [
     (7599, 64, 64, 15),       # cfg2
     (242429 // 4, 64, 64, 15),  # a batch of clouds: many vertex ranges per CTA column

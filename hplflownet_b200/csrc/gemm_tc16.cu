@@ -104,10 +104,13 @@ __global__ void absmax_tail_kernel(const float* __restrict__ x, long long lo, lo
 
 // ------------------------------------------------------------------------------ weight image
 // w (F, C, Co) fp32 -> per (N tile, K block of 32) [hi 4 KB | lo 4 KB] in the shared-memory layout.
+template <int TNv>
 __global__ void weight_image16_kernel(const float* __restrict__ w, int filter_size, int c_in, int c_out, int kb_per_tap,
                                       const uint32_t* __restrict__ w_amax, uint8_t* __restrict__ image) {
+    constexpr int TN = TNv;
+    constexpr int kBHalf = TN * TK * 2;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    constexpr int chunks = TN * (TK / 8);                                  // 256 16-byte chunks per K block
+    constexpr int chunks = TN * (TK / 8);                                  // 16-byte chunks per K block
     const long long n_kb = (long long)filter_size * kb_per_tap;
     const long long n_tiles = (c_out + TN - 1) / TN;
     if (t >= n_tiles * n_kb * chunks) return;
@@ -133,13 +136,19 @@ __global__ void weight_image16_kernel(const float* __restrict__ w, int filter_si
 }
 
 // ------------------------------------------------------------------------------ forward / dgrad
-template <bool I64>
+template <bool I64, int TNv, int kStagesV>
 __global__ void __launch_bounds__(kThreads, 2)
 gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_rows, const void* __restrict__ nbr,
                        int filter_size, long long n_out_rows, int c_in, int c_out, int kb_per_tap,
                        const uint8_t* __restrict__ w_image, const float* __restrict__ bias, int act, float* __restrict__ out,
                        long long ld_out, int out_cm, int n_main, const uint32_t* __restrict__ in_amax,
                        const uint32_t* __restrict__ w_amax) {
+    // tile width (64 for narrow layers, 128 for Co >= 128: half as many re-gathers of A) and ring depth
+    constexpr int TN = TNv, kStages = kStagesV;
+    constexpr int kBHalf = TN * TK * 2;
+    constexpr int kStageBytes = 2 * kAHalf + 2 * kBHalf;
+    constexpr uint32_t kB_LBO = TN * 16;
+    constexpr uint32_t kIdescK = instr_desc(0, TM, TN, 0, 0);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], accum_bar;
@@ -549,8 +558,10 @@ wgrad_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_r
 void set_attrs() {
     static bool done = false;
     if (done) return;
-    cudaFuncSetAttribute(gather_gemm_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    cudaFuncSetAttribute(gather_gemm_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaFuncSetAttribute(gather_gemm_f16_kernel<true, 64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaFuncSetAttribute(gather_gemm_f16_kernel<false, 64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaFuncSetAttribute(gather_gemm_f16_kernel<true, 128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (2 * kAHalf + 2 * 128 * TK * 2) + 1024);
+    cudaFuncSetAttribute(gather_gemm_f16_kernel<false, 128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (2 * kAHalf + 2 * 128 * TK * 2) + 1024);
     cudaFuncSetAttribute(wgrad_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmemBytes);
     cudaFuncSetAttribute(wgrad_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmemBytes);
     done = true;
@@ -578,8 +589,8 @@ int hpl_absmax(const float* x, int64_t count, uint32_t* out_bits, void* stream) 
 }
 
 int64_t hpl_blur_gemm_f16_workspace(int64_t filter_size, int64_t c_in, int64_t c_out) {
-    const int64_t kb_per_tap = (c_in + TK - 1) / TK, n_tiles = (c_out + TN - 1) / TN;
-    return n_tiles * filter_size * kb_per_tap * 2 * kBHalf + 16;       // image + the weight absmax slot
+    const int64_t kb_per_tap = (c_in + TK - 1) / TK, n_cols = (c_out + 127) / 128 * 128;       // covers both tile widths
+    return n_cols * filter_size * kb_per_tap * 2 * (TK * 2) + 16;      // image + the weight absmax slot
 }
 
 int hpl_blur_gemm_f16(const float* in, int64_t ld_in, int64_t n_in_rows, const void* nbr, int idx64, int64_t filter_size,
@@ -594,24 +605,34 @@ int hpl_blur_gemm_f16(const float* in, int64_t ld_in, int64_t n_in_rows, const v
     cudaStream_t s = as_stream(stream);
     set_attrs();
     const int kb_per_tap = (int)((c_in + TK - 1) / TK);
-    const long long n_tiles = (c_out + TN - 1) / TN;
-    const long long image_bytes = n_tiles * filter_size * kb_per_tap * 2 * kBHalf;
+    const bool wide = c_out >= 128;                          // N = 128 tiles: the gathered operand is staged half as often
+    const int tn = wide ? 128 : 64;
+    const long long n_tiles = (c_out + tn - 1) / tn;
+    const long long image_bytes = n_tiles * filter_size * kb_per_tap * 2 * (tn * TK * 2);
     uint8_t* image = reinterpret_cast<uint8_t*>(workspace);
     uint32_t* w_amax = reinterpret_cast<uint32_t*>(image + image_bytes);
     const long long w_count = filter_size * c_in * c_out;
     const int rc = hpl_absmax(w, w_count, w_amax, stream);
     if (rc != 0) return rc;
-    const long long chunks = n_tiles * filter_size * kb_per_tap * (TN * (TK / 8));
-    weight_image16_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, s>>>(w, (int)filter_size, (int)c_in, (int)c_out, kb_per_tap, w_amax, image);
-    const long long steps = (long long)filter_size * kb_per_tap * (TK / 16);
-    const int n_main = steps <= 160 ? 1 : (steps <= 480 ? 3 : 7);
-    dim3 grid((unsigned)((n_out_rows + TM - 1) / TM), (unsigned)n_tiles);
-    if (idx64)
-        gather_gemm_f16_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, (int)c_in, (int)c_out,
-                                                                        kb_per_tap, image, bias, act, out, ld_out, out_channel_major, n_main, in_amax, w_amax);
+    const long long chunks = n_tiles * filter_size * kb_per_tap * (tn * (TK / 8));
+    if (wide)
+        weight_image16_kernel<128><<<(unsigned)((chunks + 255) / 256), 256, 0, s>>>(w, (int)filter_size, (int)c_in, (int)c_out, kb_per_tap, w_amax, image);
     else
-        gather_gemm_f16_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, (int)c_in, (int)c_out,
-                                                                         kb_per_tap, image, bias, act, out, ld_out, out_channel_major, n_main, in_amax, w_amax);
+        weight_image16_kernel<64><<<(unsigned)((chunks + 255) / 256), 256, 0, s>>>(w, (int)filter_size, (int)c_in, (int)c_out, kb_per_tap, w_amax, image);
+    const long long steps = (long long)filter_size * kb_per_tap * (TK / 16);
+    // accumulate steps per hi.hi accumulator <= ~160-190; TMEM holds (n_main + 1) * tn <= 512 columns
+    const int n_main = steps <= 160 ? 1 : ((steps <= 480 || wide) ? 3 : 7);
+    dim3 grid((unsigned)((n_out_rows + TM - 1) / TM), (unsigned)n_tiles);
+#define HPL_LAUNCH_F16(I64, TNV, ST)                                                                                         \
+    gather_gemm_f16_kernel<I64, TNV, ST><<<grid, kThreads, ST * (2 * kAHalf + 2 * TNV * TK * 2) + 1024, s>>>(                \
+        in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, (int)c_in, (int)c_out, kb_per_tap, image, bias, act, out,   \
+        ld_out, out_channel_major, n_main, in_amax, w_amax)
+    if (wide) {
+        if (idx64) HPL_LAUNCH_F16(true, 128, 3); else HPL_LAUNCH_F16(false, 128, 3);
+    } else {
+        if (idx64) HPL_LAUNCH_F16(true, 64, 4); else HPL_LAUNCH_F16(false, 64, 4);
+    }
+#undef HPL_LAUNCH_F16
     HPL_RETURN_LAST();
 }
 

@@ -3,8 +3,8 @@
 Same constructor argument object, ``forward(pc1, pc2, generated_data)`` signature, module names and
 ``state_dict`` layout as ``models/HPLFlowNet.py:11-430`` so reference checkpoints load with
 ``strict=True``; the wiring is expressed as data (tables of layer widths) instead of the reference's
-unrolled code.  The pointwise ``Conv1d`` stacks (``conv1``, ``conv2-4``) are stock PyTorch ops as in
-the reference; every bilateral / correlation layer runs the hand-written CUDA path.
+unrolled code.  Every layer -- bilateral, correlation and the pointwise ``Conv1d`` stacks (``conv1``,
+``conv2-4``, via ``pointwise.py``) -- runs the hand-written CUDA path; the modules only hold parameters.
 """
 import torch
 import torch.nn as nn
@@ -12,6 +12,7 @@ import torch.nn as nn
 from .bilateralNN import BilateralConvFlex
 from .bnn_flow import BilateralCorrelationFlex
 from .module_utils import Conv1dReLU
+from .pointwise import pointwise_stack
 
 __all__ = ["HPLFlowNet"]
 
@@ -62,13 +63,10 @@ class HPLFlowNet(nn.Module):
         self.conv4 = nn.Conv1d(512, 3, kernel_size=1)
 
     def forward(self, pc1, pc2, generated_data):
-        # the stock pointwise convs must stay fp32: PyTorch lets cuDNN use TF32 for convolutions by default
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            return self._forward(pc1, pc2, generated_data)
-
-    def _forward(self, pc1, pc2, generated_data):
         gd = generated_data
-        down1, down2 = [self.conv1(pc1)], [self.conv1(pc2)]          # HPLFlowNet.py:239-240
+        # pointwise Conv1d stacks run on the same tensor-core GEMM (fp32-accurate; cuDNN would use TF32 by default)
+        down1 = [pointwise_stack(self.conv1, pc1)]                   # HPLFlowNet.py:239-240
+        down2 = [pointwise_stack(self.conv1, pc2)]
         corr = [None] * N_SCALES
         prev_corr = None
         for k in range(N_SCALES):                                    # :242-369
@@ -104,4 +102,4 @@ class HPLFlowNet(nn.Module):
                 torch.cat(parts, dim=1), in_barycentric=None, in_lattice_offset=None,
                 blur_neighbors=gd[k]["pc1_blur_neighbors"], out_barycentric=gd[k]["pc1_barycentric"],
                 out_lattice_offset=gd[k]["pc1_lattice_offset"])
-        return self.conv4(self.conv3(self.conv2(up)))                # :426-428
+        return pointwise_stack((self.conv2, self.conv3, self.conv4), up)     # :426-428

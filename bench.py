@@ -301,6 +301,9 @@ def run_ours(args):
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d2h = 4 + sum(p.numel() * 4 for p in params)
 
+    # ---- secondary, all ranks: data-parallel HPLFlowNet training step (BASELINE configs[4])
+    train = train_leg(dev, rank, world)
+
     # ---- max over ranks
     ms, e2e_s = sharding.max_over_ranks([ms, e2e_s], device=dev)
     if rank != 0:
@@ -362,10 +365,78 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "clouds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps},
         "gpu_launches": launches, "clocks": clocks, "lattice_build": lattice, "model_forward": model_fwd,
+        "train_step": train,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+TRAIN_PAIRS_PER_STEP = 8
+
+
+def train_leg(dev, rank, world, steps=4, warmup=2):
+    """Secondary number (BASELINE configs[4]): one data-parallel optimisation step of the full
+    HPLFlowNet -- 8 synthetic 8192+8192-pt pairs per step in total, sharded over the ranks (strong scaling,
+    8/N pairs per GPU), lattice built on the GPU per pair, EPE3D loss, backward, ONE flat NCCL all-reduce of
+    the 19.3 M gradients, Adam.  Called by every rank; timed with CUDA events, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from hplflownet_b200 import sharding, train as T
+    from hplflownet_b200.HPLFlowNet import HPLFlowNet
+    from hplflownet_b200.synthetic import frustum_pair
+    from hplflownet_b200.transforms import GenerateDataUnsymmetric, collate_batch1
+
+    class A:
+        dim = 3
+        evaluate = False
+        use_leaky = bcn_use_bias = bcn_use_norm = True
+        last_relu = False
+        DEVICE = "cuda"
+        scales_filter_map = [[3., 1, -1, -1], [2., 1, -1, -1], [1., 1, 1, 1], [.5, 1, 1, 1], [.25, 1, 1, 1],
+                             [.125, 1, 1, 1], [.0625, 1, 1, 1]]
+    if TRAIN_PAIRS_PER_STEP % world:
+        return {"skipped": "world size %d does not divide %d pairs" % (world, TRAIN_PAIRS_PER_STEP)}
+    ok, err, model, opt, gen, pairs = 1, None, None, None, None, None
+    try:
+        torch.manual_seed(0)                                     # same initial weights on every rank
+        model = HPLFlowNet(A()).to(dev).train()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4)     # main.py:118, configs/train_ours.yaml
+        gen = GenerateDataUnsymmetric(A(), device=dev, index_dtype=torch.int32)
+        local = TRAIN_PAIRS_PER_STEP // world
+        pairs = []
+        for i in range(local):
+            pc1, pc2 = frustum_pair(N_POINTS, 500 + rank * local + i)
+            pairs.append((pc1, pc2, (pc2 - pc1).astype("float32")))
+        # dry run of the local part (no collective) so that a failure cannot leave the other ranks waiting
+        p1, p2, sf, gd = gen(list(pairs[0]))
+        T.epe3d_loss(model(p1[None], p2[None], collate_batch1(gd)), sf[None]).backward()
+        torch.cuda.synchronize()
+    except Exception as e:                                       # noqa: BLE001 -- secondary leg must not kill the bench
+        ok, err = 0, "%s: %s" % (type(e).__name__, e)
+    if world > 1:
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = int(flag.item()) if ok else 0
+    if not ok:
+        return {"error": err or "failed on another rank"}
+    for _ in range(warmup):
+        T.train_step(model, opt, gen, pairs, collate_batch1)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = T.train_step(model, opt, gen, pairs, collate_batch1)
+    e1.record()
+    torch.cuda.synchronize()
+    (ms,) = sharding.max_over_ranks([e0.elapsed_time(e1)], device=dev)
+    return {"workload": "HPLFlowNet train step: %d pairs (8192+8192 pts, 7 scales) per step over %d GPU(s), GPU lattice "
+                        "build + forward + EPE3D + backward + flat gradient all-reduce + Adam" % (TRAIN_PAIRS_PER_STEP, world),
+            "value": TRAIN_PAIRS_PER_STEP * steps / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms / steps,
+            "scaling": "strong", "steps": steps, "warmup": warmup, "loss_finite": bool(torch.isfinite(loss)),
+            "params": sum(p.numel() for p in model.parameters())}
 
 
 def model_leg(dev):

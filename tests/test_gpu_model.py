@@ -48,3 +48,37 @@ def test_pointwise_stack_matches_torch_conv1d():
     assert_close(got[0], want[0], "output")
     for a, b in zip(got[1:], want[1:]):
         assert_close_grad(a, b, "grad")
+
+
+def test_model_backward_matches_float64_oracle():
+    # whole-network gradients (the cfg5 training step's backward): CUDA path vs the oracle in float64
+    from oracle import hplflownet as OM
+    from oracle import lattice as OL
+    from tests._util import assert_close_grad
+    g = golden("model_frustum256.npz")
+    model = name_keyed_init_(HPLFlowNet(ModelArgs()), int(g["seed"]))
+    state = {k: (v.detach().clone().double().requires_grad_(True) if v.is_floating_point() else v.clone())
+             for k, v in model.state_dict().items()}
+    gd_np = OL.generate(g["pc1"], g["pc2"], ModelArgs.scales_filter_map)
+    gd_ref = [{k: (torch.from_numpy(v)[None] if not isinstance(v, int) else v) for k, v in d.items()} for d in gd_np]
+    gd_ref = [{k: (v.double() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in d.items()} for d in gd_ref]
+    p1, p2 = [torch.from_numpy(np.ascontiguousarray(g[k].T))[None] for k in ("pc1", "pc2")]
+    target = torch.from_numpy(np.ascontiguousarray((g["pc2"] - g["pc1"]).T))[None]
+    out_ref = OM.forward(state, p1.double(), p2.double(), gd_ref)
+    loss_ref = torch.norm(out_ref - target.double(), p=2, dim=1).mean()        # EPE3D loss, models/epe3d_loss.py:9
+    loss_ref.backward()
+
+    model = model.cuda().train()
+    gen = GenerateDataUnsymmetric(ModelArgs())
+    pc1, pc2, sf, gd = gen([g["pc1"], g["pc2"], g["pc2"] - g["pc1"]])
+    out = model(pc1[None], pc2[None], collate_batch1(gd))
+    loss = torch.norm(out - sf[None], p=2, dim=1).mean()
+    loss.backward()
+    assert_close(loss.detach(), loss_ref.detach(), "loss")
+    checked = 0
+    for name, p in model.named_parameters():
+        if p.grad is None:
+            continue
+        assert_close_grad(p.grad, state[name].grad, "grad " + name)
+        checked += 1
+    assert checked >= 100

@@ -67,3 +67,39 @@ def test_reference_arm_only_rank0_prints():
     assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["unit"] == "clouds/s"
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
     assert line["value"] > 0
+
+
+def _grad_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hplflownet_b200.train import allreduce_mean_grads_
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
+    frozen = torch.nn.Parameter(torch.ones(4), requires_grad=False)
+    x = torch.full((2, 5), float(rank + 1))
+    net(x).sum().backward()
+    net[1].bias.grad = None                                  # a parameter without gradient on this rank
+    n = allreduce_mean_grads_(list(net.parameters()) + [frozen])
+    torch.save({"n": n, "grads": [p.grad.clone() for p in net.parameters()]}, os.path.join(out_dir, "g%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_averages_over_ranks(tmp_path):
+    world, port = 2, 29615
+    mp.spawn(_grad_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(tmp_path / ("g%d.pt" % r)) for r in range(world)]
+    assert res[0]["n"] == 5 * 7 + 7 + 7 * 3 + 3
+    for a, b in zip(res[0]["grads"], res[1]["grads"]):
+        assert torch.equal(a, b)                             # identical on every rank after the all-reduce
+    # expected: mean over ranks of the single-rank gradients (inputs 1 and 2 -> weight grads scale linearly)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
+    grads = []
+    for r in range(world):
+        net.zero_grad()
+        net(torch.full((2, 5), float(r + 1))).sum().backward()
+        grads.append([p.grad.clone() for p in net.parameters()])
+    want = [(a + b) / 2 for a, b in zip(*grads)]
+    want[3] = torch.zeros_like(want[3])                      # bias grad was dropped on both ranks -> zeros
+    for got, w in zip(res[0]["grads"], want):
+        assert torch.allclose(got, w, rtol=1e-6, atol=1e-7)

@@ -32,6 +32,10 @@ SIGNATURES = {
     "hpl_split16": [vp, i64, i64, i64, vp, vp, vp],
     "hpl_blur_gemm_p16": [vp, i64, vp, cint, i64, i64, i64, i64, vp, vp, cint, vp, i64, cint, vp, vp, vp],
     "hpl_blur_wgrad_p16": [vp, i64, vp, cint, i64, i64, i64, i64, vp, vp, vp, vp, vp],
+    "hpl_h16_bytes": [i64, i64],
+    "hpl_h16_split": [vp, i64, i64, i64, vp, vp, vp],
+    "hpl_blur_gemm_tma_workspace": [i64, i64, i64],
+    "hpl_blur_gemm_tma": [vp, i64, vp, cint, i64, i64, i64, i64, vp, vp, cint, vp, i64, cint, vp, vp, vp],
     "hpl_column_sums": [vp, i64, i64, i64, vp, vp],
     "hpl_act_backward": [vp, i64, vp, i64, i64, i64, cint, vp],
     "hpl_transpose_table": [vp, cint, i64, i64, vp, i64, vp, vp],
@@ -54,12 +58,12 @@ SIGNATURES = {
 
 
 RETURNS_I64 = {"hpl_lattice_table_capacity", "hpl_lattice_scan_blocks", "hpl_blur_gemm_tc_workspace",
-               "hpl_blur_gemm_f16_workspace", "hpl_split16_bytes"}   # sizes, not status codes
+               "hpl_blur_gemm_f16_workspace", "hpl_split16_bytes", "hpl_h16_bytes", "hpl_blur_gemm_tma_workspace"}   # sizes, not status codes
 
 # kernels enqueued per call (for bench.py's gpu_launches claim)
 LAUNCHES = {
     "hpl_scatter_rows": 1, "hpl_normalize_rows": 2, "hpl_gather_rows": 1, "hpl_blur_gemm": 1, "hpl_blur_gemm_tc": 2,
-    "hpl_blur_wgrad": 2, "hpl_blur_wgrad_tc": 2, "hpl_absmax": 1, "hpl_split16": 1, "hpl_blur_gemm_p16": 3, "hpl_blur_wgrad_p16": 1, "hpl_blur_gemm_f16": 3, "hpl_blur_wgrad_f16": 2, "hpl_act_backward": 1, "hpl_transpose_table": 1, "hpl_cm_to_rows": 1,
+    "hpl_blur_wgrad": 2, "hpl_blur_wgrad_tc": 2, "hpl_absmax": 1, "hpl_split16": 1, "hpl_h16_split": 1, "hpl_blur_gemm_tma": 3, "hpl_blur_gemm_p16": 3, "hpl_blur_wgrad_p16": 1, "hpl_blur_gemm_f16": 3, "hpl_blur_wgrad_f16": 2, "hpl_act_backward": 1, "hpl_transpose_table": 1, "hpl_cm_to_rows": 1,
     "hpl_rows_to_cm": 1, "hpl_channel_sums": 1, "hpl_fill_zero": 1, "hpl_fill_i32": 1,
     "hpl_corr_gather": 1, "hpl_corr_scatter": 1, "hpl_column_sums": 1,
     "hpl_lattice_init_range": 1, "hpl_lattice_points": 1, "hpl_lattice_insert": 6,

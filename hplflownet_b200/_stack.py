@@ -19,7 +19,11 @@ def forward(x, c_in, n_rows, layers, first_nbr=None, last_channel_major=False, f
         scale = first_row_scale if l == 0 else None
         split = ops.DEFAULT_PRECISION >= 2 and scale is None and chans[-1] % 4 == 0
         amax = ops.absmax(xs[-1]) if split else None
-        x16 = ops.split16(xs[-1], chans[-1], amax) if (split and ops.DEFAULT_PRECISION == 3) else None
+        x16 = None
+        if split and ops.DEFAULT_PRECISION == 3:
+            x16 = ops.split16(xs[-1], chans[-1], amax)
+        elif split and ops.DEFAULT_PRECISION == 4:
+            x16 = ops.h16_split(xs[-1], chans[-1], amax)
         amaxs.append((amax, x16))
         y = ops.blur_gemm(xs[-1], chans[-1], first_nbr if l == 0 else None, n_rows, w, b,
                           act, out_channel_major=direct_cm, row_scale=scale, x_amax=amax, x16=x16)
@@ -45,7 +49,11 @@ def backward(dx, xs, chans, layers, n_rows, first_nbr, first_nbr_t, need_input_g
         tbl = first_nbr if l == 0 else None
         split = ops.DEFAULT_PRECISION >= 2 and chans[l + 1] % 4 == 0
         dz_amax = ops.absmax(dx) if split else None                          # shared by wgrad and dgrad
-        dz16 = ops.split16(dx, chans[l + 1], dz_amax) if (split and ops.DEFAULT_PRECISION == 3) else None
+        dz16 = None
+        if split and ops.DEFAULT_PRECISION == 3:
+            dz16 = ops.split16(dx, chans[l + 1], dz_amax)
+        elif split and ops.DEFAULT_PRECISION == 4 and (l > 0 or need_input_grad):
+            dz16 = ops.h16_split(dx, chans[l + 1], dz_amax)
         x_amax, x16 = amaxs[l] if amaxs else (None, None)
         if need_param_grad[l]:
             grads[l] = ops.blur_wgrad(xs[l], chans[l], tbl, n_rows, dx, chans[l + 1], w.size(0), want_db=b is not None,

@@ -10,7 +10,9 @@ from . import _lib
 
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 
-# Contraction engine: 2 = tcgen05 with a scaled FP16 hi/lo split done in registers per tap ("3xFP16", half
+# Contraction engine: 4 = tcgen05 3xFP16 with operands pre-split once in HBM and moved by TMA row gathers
+# (cp.async.bulk.tensor ... tile::gather4; csrc/gemm_tma.cu; forward / data gradient, dW uses engine 2),
+# 2 = tcgen05 with a scaled FP16 hi/lo split done in registers per tap ("3xFP16", half
 # the operand bytes; default), 3 = same math with operands pre-split once in HBM and copied by cp.async
 # (parity-green, currently slower -- see csrc/gemm_tc16p.cu),
 # 1 = tcgen05 with 3xTF32 compensation, 0 = fp32 FMA on CUDA cores (parity anchor).  All are hand-written
@@ -121,6 +123,15 @@ def split16(x, channels, amax):
     return buf
 
 
+def h16_split(x, channels, amax):
+    """fp16 hi/lo row image for the TMA-gathered contraction (include/hplflownet_b200.h: hpl_h16_split)."""
+    _f32(x, "x")
+    n = x.size(0)
+    buf = torch.empty(_lib.load().hpl_h16_bytes(n, channels), dtype=torch.uint8, device=x.device)
+    _lib.call("hpl_h16_split", x.data_ptr(), x.stride(0), n, channels, amax.data_ptr(), buf.data_ptr(), _stream())
+    return buf
+
+
 def tc_path(c_in, precision=None):
     """True when the tensor-core kernels (which can fold ``row_scale``) will run for this operand."""
     return (DEFAULT_PRECISION if precision is None else precision) >= 1 and c_in % 4 == 0
@@ -157,13 +168,24 @@ def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_majo
     if precision is None:
         precision = DEFAULT_PRECISION
     bias_ptr = bias.data_ptr() if bias is not None else None
+    if precision == 4 and (c % 4 != 0 or row_scale is not None):
+        precision = 1
     if precision == 3 and (c % 4 != 0 or row_scale is not None):
         precision = 1
     if precision == 2 and (c % 4 != 0 or row_scale is not None):
         precision = 1
     if precision == 1 and c % 4 != 0:
         precision = 0
-    if precision == 3:
+    if precision == 4:
+        ws = _workspace(x.device, _lib.load().hpl_blur_gemm_tma_workspace(f, c, co))
+        if x16 is None:
+            x_amax = absmax(x)
+            x16 = h16_split(x, c, x_amax)
+        with _timed(tag):
+            _lib.call("hpl_blur_gemm_tma", x16.data_ptr(), x.size(0), nbr_ptr, i64, f, n_out_rows, c, co,
+                      w.data_ptr(), bias_ptr, act, out.data_ptr(), out.stride(0), int(out_channel_major),
+                      ws.data_ptr(), x_amax.data_ptr(), _stream())
+    elif precision == 3:
         ws = _workspace(x.device, _lib.load().hpl_blur_gemm_f16_workspace(f, c, co))
         if x16 is None:
             x_amax = absmax(x)
@@ -208,6 +230,8 @@ def blur_wgrad(x, c_in, nbr, n_out_rows, dz, c_out, filter_size, want_db=True, p
     db = torch.zeros(c_out, dtype=torch.float32, device=x.device) if want_db else None
     if precision is None:
         precision = DEFAULT_PRECISION
+    if precision == 4:                       # the TMA engine covers forward / data gradient; dW stays register-staged
+        precision, x16, dz16 = 2, None, None
     if precision == 3 and c_in % 32 == 0 and row_scale is None:
         if x16 is None:
             x_amax = absmax(x)

@@ -153,6 +153,24 @@ int hpl_blur_wgrad_p16(const void* in16, int64_t n_in_rows, const void* nbr, int
                        const void* dz16, float* dw, const uint32_t* in_amax, const uint32_t* dz_amax,
                        void* stream);
 
+/* TMA-gathered variant (csrc/gemm_tma.cu): same contraction as hpl_blur_gemm_f16 (replaces the advanced-index
+ * gather + Conv2d of models/bilateralNN.py:198-221), but the gathered operand is moved by the Tensor Memory
+ * Accelerator (cp.async.bulk.tensor ... tile::gather4, four lattice rows per instruction, written straight into
+ * the SWIZZLE_128B operand layout of tcgen05.mma) by a persistent one-CTA-per-SM kernel with no producer warps.
+ *   hpl_h16_split(x, ld, n_rows, C, amax, x16): x16 = (n_rows + 1) rows of [hi(ld16) | lo(ld16)] fp16,
+ *     ld16 = round8(C); x / s = hi + lo * 2^-11 with s the power of two derived from `amax` (hpl_absmax); the last
+ *     row is zero (missing neighbours are redirected to it).  hpl_h16_bytes gives the size; x16 16-byte aligned.
+ *   hpl_blur_gemm_tma: `in16` is that image of the (n_in_rows, c_in) input; everything else as hpl_blur_gemm_f16;
+ *     workspace of hpl_blur_gemm_tma_workspace(F, C, Co) bytes, 128-byte aligned. */
+int64_t hpl_h16_bytes(int64_t n_rows, int64_t channels);
+int hpl_h16_split(const float* x, int64_t ld, int64_t n_rows, int64_t channels, const uint32_t* amax,
+                  void* x16, void* stream);
+int64_t hpl_blur_gemm_tma_workspace(int64_t filter_size, int64_t c_in, int64_t c_out);
+int hpl_blur_gemm_tma(const void* in16, int64_t n_in_rows, const void* nbr, int idx64,
+                      int64_t filter_size, int64_t n_out_rows, int64_t c_in, int64_t c_out,
+                      const float* w, const float* bias, int act, float* out, int64_t ld_out,
+                      int out_channel_major, void* workspace, const uint32_t* in_amax, void* stream);
+
 /* sums[c] += sum_v rows[v, c]  (conv bias gradients). rows (n_rows, ld) vertex-major. */
 int hpl_column_sums(const float* rows, int64_t ld, int64_t n_rows, int64_t channels, float* sums,
                     void* stream);

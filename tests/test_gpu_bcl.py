@@ -166,3 +166,27 @@ def test_fused_normalisation_matches_unfused():
     assert_close_grad(res[1][1], res[0][1], "grad_features")
     for a, b in zip(res[1][2], res[0][2]):
         assert_close_grad(a, b, "param grad")
+
+
+def test_bcl_tma_engine_matches_default_engine(monkeypatch):
+    """Whole layer forward + backward with the contraction engine switched to 4 (TMA / cp.async staged, operands
+    pre-split once per tensor) against the default engine: same results to fp32 rounding."""
+    from hplflownet_b200 import ops
+    d = _lattice(8192, 5, 1.0)
+    torch.manual_seed(0)
+    mod = hpl.BilateralConvFlex(3, 1, 64, [64, 32], "cuda", use_bias=True, use_leaky=True, use_norm=True,
+                                do_splat=True, do_slice=True, last_relu=False, chunk_size=-1).to(DEV)
+    feat = torch.randn(1, 64, 8192, device=DEV)
+    gy = torch.randn(1, 32, 8192, device=DEV)
+    bary, off, nbr = d["pc1_barycentric"].to(DEV), d["pc1_lattice_offset"].to(DEV), d["pc1_blur_neighbors"].to(DEV)
+    res = {}
+    for engine in (2, 4):
+        monkeypatch.setattr(ops, "DEFAULT_PRECISION", engine)
+        f = feat.clone().requires_grad_(True)
+        for p in mod.parameters():
+            p.grad = None
+        y = mod(f, bary, off, nbr, bary, off)
+        y.backward(gy)
+        res[engine] = [y.detach().clone(), f.grad.clone()] + [p.grad.clone() for p in mod.parameters()]
+    for a, b in zip(res[4], res[2]):
+        assert_close(a, b, "engine 4 vs engine 2")

@@ -1,31 +1,46 @@
-// TMA-gathered 3xFP16 gather-GEMM: the blur / data-gradient contraction with NO producer warps.
+// Engine 4: "split once, copy many" 3xFP16 gather-GEMM (blur forward / data gradient) as a PERSISTENT kernel whose
+// operands are staged by the copy engines -- TMA and cp.async -- instead of by converting producer warps.
 //
-// ncu on the register-staged kernels (gemm_tc16.cu) showed them paced by instruction issue: eight producer
-// warps LDG the gathered rows, split every element into fp16 hi/lo once per tap (15x) and STS them into the
-// UMMA layout; the tensor pipe idles at ~20 %.  Here the split happens ONCE per tensor (hpl_h16_split) and the
-// rows are moved by the Tensor Memory Accelerator's row-gather mode:
+// ncu on the register-staged kernels (gemm_tc16.cu) showed them paced by instruction issue: eight producer warps LDG
+// the gathered rows, split every element into fp16 hi/lo once per tap (15x) and STS them into the UMMA layout; the
+// tensor pipe idles at ~20 %.  Here the split happens ONCE per tensor (hpl_h16_split) and shared memory is filled by
+//   * cp.async (LDGSTS, 16 bytes, zero-fill) -- a quarter warp moves one 128-byte line (one plane of one gathered row)
+//     straight into its SWIZZLE_128B position; completion is reported asynchronously to the stage's mbarrier
+//     (cp.async.mbarrier.arrive.noinc), so producers never wait for their own copies;
+//   * the Tensor Memory Accelerator: one cp.async.bulk per weight block, 128 x 64 tile loads for the un-gathered 1x1
+//     layers, and -- optionally, HPL_TMA_WARPS -- its row-gather mode for the gathered rows,
+//       cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4      (UTMALDG.2D.GATHER4 in SASS)
+//     which takes FOUR row indices per instruction and writes the four 128-byte rows in the SWIZZLE_128B pattern, i.e.
+//     exactly the K-major operand layout tcgen05.mma consumes.  A missing neighbour (-1) is redirected to an all-zero
+//     row appended to the image.
 //
-//   cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4   (UTMALDG.2D.GATHER4 in SASS)
+// CTA = persistent worker, one per SM (~225 KB of shared memory), work item = (128-vertex tile, N tile):
+//   warps 0-7   A producers : stage ring of 5 (N = 64) / 4 (N = 128) x 32 KB (hi plane | lo plane, 64 channels);
+//                             the tile's whole index block (F x 128 entries) sits in shared memory one item ahead
+//   warp 9      B producer  : pre-split, pre-swizzled weight image, one cp.async.bulk per (tap, 64-channel block)
+//   warp 14     fence relay : cp.async writes through the generic proxy and completes asynchronously, tcgen05.mma reads
+//                             through the async proxy: this warp waits for a full stage, executes fence.proxy.async and
+//                             hands the stage to the issuer (keeps the MEMBAR out of the pacing thread)
+//   warp 8      MMA issuer  : lane 0, tcgen05.mma.cta_group::1.kind::f16 M128 x N{64,128} x K16, three MMAs per K step
+//                             (lo.hi + hi.lo into a cross accumulator, hi.hi into 1/3/7 main accumulators)
+//   warps 10-13 epilogue    : tcgen05.ld, scales, bias, activation, stores -- overlapped with the next work item
+//                             through double-buffered TMEM accumulators when 512 columns allow
 //
-// which takes FOUR row indices per instruction and writes the four rows (64 halves = 128 bytes each) into
-// shared memory in the SWIZZLE_128B pattern -- exactly the K-major operand layout tcgen05.mma consumes.  Four
-// warps issue the 2 x 32 gather4 of a 128-vertex x 64-channel stage (hi and lo plane); no LDG, no conversion, no
-// STS, no staging registers.  A missing neighbour (-1) is redirected to an all-zero row appended to the image.
-//
-// CTA = persistent worker, one per SM (~225 KB of shared memory):
-//   warps 0-3   A producers: neighbour indices -> gather4 into a 5-stage ring (32 KB per stage: hi | lo)
-//   warp 5      B producer : pre-split, pre-swizzled weight image, one cp.async.bulk per 64-channel block
-//   warp 4      MMA issuer : lane 0, tcgen05.mma.cta_group::1.kind::f16 M128 x N{64,128} x K16, three MMAs per
-//                            K step (lo.hi + hi.lo into a cross accumulator, hi.hi into 1/3/7 main accumulators)
-//   warps 6-9   epilogue   : tcgen05.ld, scales, bias, activation, stores -- overlapped with the next work item
-//                            through double-buffered TMEM accumulators
-// A work item is a GROUP of G consecutive 128-vertex tiles that share every weight block (the weight image is
-// streamed once per group instead of once per tile: L2 -> SM traffic of B drops by G).
+// Measured on B200 (cfg2 x 32 clouds, H = 242 429; 64 -> 64 channels; tools/try_tma.py):
+//   * TMA gather4 alone: 0.31 ms.  The TMA unit retires about one gather4 (512 bytes) per ~48 cycles per SM whatever the
+//     number of issuing warps: ~3 TB/s over the chip, below the ~5.8 TB/s the LSU paths reach on the same rows.
+//   * cp.async alone: 0.25 ms -- on par with the register-staged engine 2 (0.25 ms in the same harness), hybrids no
+//     better.  Ablations (loads off / MMAs off / both): every variant of the L2 -> SM gather tops out near 5.8-5.9 TB/s
+//     (ncu: L2 13 % busy, L1 19 %, tensor pipe 14 %, nothing saturated): the pattern, not the staging mechanism, is the
+//     limit, so the next step is fewer L2 -> SM bytes (vertex re-ordering for shared-memory reuse across taps), see
+//     DESIGN.md.  Pitfalls found on the way: a per-tap dependent index load cost 150 us (hence the shared-memory index
+//     block), a 64-bit division per K step in the issuer thread another 40 us.
+//   * Since engine 4 needs two extra split passes (21 us each) per layer and direction, engine 2 stays the default.
 //
 // h16 image of a vertex-major fp32 matrix x (n_rows, C):  (n_rows + 1) rows of [ hi(ld16) | lo(ld16) ] halves,
 // ld16 = round8(C), x / s = hi + lo * 2^-11 (s: per-tensor power of two from hpl_absmax, as in gemm_tc16.cu);
 // row n_rows is zero.  Two tensor maps (hi plane, lo plane) view it as (n_rows + 1) x C with a 4 * ld16-byte row
-// pitch; channels beyond C are zero-filled by the TMA unit (out-of-bounds box columns).
+// pitch; channels beyond C are zero-filled by the TMA unit (out-of-bounds box columns) or by cp.async (src-size 0).
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -88,19 +103,6 @@ __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity) {
             : "memory");
         if (spins > (1u << 26)) __trap();
     }
-}
-
-// one lane of a converged warp (ptxas then issues the guarded tcgen05 instructions without a per-lane loop)
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "elect.sync _|p, 0xffffffff;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(pred));
-    return pred != 0;
 }
 
 __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, int col, int r0, int r1, int r2, int r3,
@@ -413,37 +415,33 @@ gather_gemm_tma_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __gri
             }
         }
     } else if (warp == kMmaWarp) {
-        // ---------------- MMA issuer.  Its instruction stream paces the CTA (ncu: ~150 scalar instructions per stage were
-        // the floor of the first version), so everything per stage is incremental -- no division / modulo -- and the
-        // descriptors are a constant high word plus a running 16-byte-unit address.  The warp runs the loop converged,
-        // lane 0 polls the barriers, one elected lane issues.
-        constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);      // SBO = 1024 B, version 1, SWIZZLE_128B
-        const int last_ksteps = min(TK / 16, (p.c_in - (p.kb_per_tap - 1) * TK + 15) / 16);
-        const bool leader = elect_one();
-        int sa = 0, sb = 0, acc = 0;
-        uint32_t pa = 0, pb = 0, pacc = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            if (lane == 0) wait_bar(acc_empty + 8 * acc, pacc ^ 1);       // epilogue has drained this accumulator set
-            __syncwarp();
-            fence_after();
-            const uint32_t tmem_cross = tmem_d + (uint32_t)(acc * acc_cols);
-            // main accumulator of K step s: g(s) = floor(s * n_main / total_steps), tracked incrementally by every lane
-            int g = 0, g_num = 0, pg = -1, cb = 0;
-            uint32_t first = 0;                                            // 0 on the very first K step of the item
-            for (int kb = 0; kb < n_kb; ++kb) {
-                const int ksteps = (cb == p.kb_per_tap - 1) ? last_ksteps : TK / 16;
-                if (++cb == p.kb_per_tap) cb = 0;
-                if (lane == 0) {
+        // ---------------- MMA issuer: one thread.  Everything per stage is incremental (no division / modulo) and the
+        // descriptors are a constant high word plus a running 16-byte-unit address.  (Measured alternatives: running the
+        // loop warp-converged with an elected issuer removes the ELECT loops ptxas wraps around every tcgen05 instruction
+        // of a lone thread, but the per-stage warp synchronisation costs as much as it saves: 0.256 ms either way on cfg2
+        // and 3.37 vs 2.87 ms on the 580 -> 1024 layer.)
+        if (lane == 0) {
+            constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
+            const int last_ksteps = min(TK / 16, (p.c_in - (p.kb_per_tap - 1) * TK + 15) / 16);
+            int sa = 0, sb = 0, acc = 0;
+            uint32_t pa = 0, pb = 0, pacc = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                wait_bar(acc_empty + 8 * acc, pacc ^ 1);                  // epilogue has drained this accumulator set
+                fence_after();
+                const uint32_t tmem_cross = tmem_d + (uint32_t)(acc * acc_cols);
+                // main accumulator of K step s: g(s) = floor(s * n_main / total_steps), tracked incrementally
+                int g = 0, g_num = 0, pg = -1, cb = 0;
+                uint32_t first = 0;                                        // 0 on the very first K step of the item
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    const int ksteps = (cb == p.kb_per_tap - 1) ? last_ksteps : TK / 16;
+                    if (++cb == p.kb_per_tap) cb = 0;
                     wait_bar(full_b + 8 * sb, pb);
                     wait_bar(ready_a + 8 * sa, pa);
-                }
-                __syncwarp();
-                fence_after();
-                const uint32_t a16 = (a_base + sa * kAStage) >> 4, b16 = (b_base + sb * C::kBStage) >> 4;
+                    fence_after();
+                    const uint32_t a16 = (a_base + sa * kAStage) >> 4, b16 = (b_base + sb * C::kBStage) >> 4;
 #pragma unroll
-                for (int j = 0; j < TK / 16; ++j) {
-                    if (j < ksteps) {
-                        if (leader) {
+                    for (int j = 0; j < TK / 16; ++j) {
+                        if (j < ksteps) {
                             const uint64_t dah = ((uint64_t)kDescHi << 32) | (a16 + 2 * j);
                             const uint64_t dal = ((uint64_t)kDescHi << 32) | (a16 + (kAPlane >> 4) + 2 * j);
                             const uint64_t dbh = ((uint64_t)kDescHi << 32) | (b16 + 2 * j);
@@ -451,24 +449,20 @@ gather_gemm_tma_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __gri
                             umma_f16(tmem_cross, dal, dbh, kIdesc, first);
                             umma_f16(tmem_cross, dah, dbl, kIdesc, 1);
                             umma_f16(tmem_cross + (uint32_t)((1 + g) * TN), dah, dbh, kIdesc, g == pg);
+                            first = 1;
+                            pg = g;
+                            g_num += p.n_main;
+                            if (g_num >= p.total_steps) { g_num -= p.total_steps; ++g; }
                         }
-                        first = 1;
-                        pg = g;
-                        g_num += p.n_main;
-                        if (g_num >= p.total_steps) { g_num -= p.total_steps; ++g; }
                     }
-                }
-                if (leader) {
                     umma_commit_a(empty_a + 8 * sa);
                     umma_commit_a(empty_b + 8 * sb);
+                    if (++sa == C::kStagesA) { sa = 0; pa ^= 1; }
+                    if (++sb == C::kStagesB) { sb = 0; pb ^= 1; }
                 }
-                __syncwarp();
-                if (++sa == C::kStagesA) { sa = 0; pa ^= 1; }
-                if (++sb == C::kStagesB) { sb = 0; pb ^= 1; }
+                umma_commit_a(acc_full + 8 * acc);
+                if (++acc == p.acc_stages) { acc = 0; pacc ^= 1; }
             }
-            if (leader) umma_commit_a(acc_full + 8 * acc);
-            __syncwarp();
-            if (++acc == p.acc_stages) { acc = 0; pacc ^= 1; }
         }
     } else {
         // ---------------- epilogue: warps 10..13 own TMEM lane quarters warp % 4

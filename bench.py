@@ -28,9 +28,9 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 METRIC = "point-clouds/sec (BCL fwd+bwd, 8192 pts, d=3, 64ch)"
-# dram__bytes_read.sum + dram__bytes_write.sum of one gather_gemm_tc_kernel launch on this workload
-# (ncu --set full, profiles/r01_tc_gemm_metrics.md); algorithmic bytes are ~139 MB.
-NCU_TRAFFIC_BYTES = 121.0e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one gather_gemm_f16_kernel (forward) launch on this workload
+# (ncu --set full, profiles/r01b_summary.md: 91.5 + 28.8 MB); algorithmic bytes are ~139 MB.
+NCU_TRAFFIC_BYTES = 120.3e6
 N_POINTS, CHANNELS, SCALE = 8192, 64, 1.0
 
 
@@ -328,10 +328,11 @@ def run_ours(args):
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
     fb, bb = algorithmic_bytes(n_tot, h_tot, CHANNELS, CHANNELS)
     all_gemm_ms = sum(a.elapsed_time(b) for _, a, b in gemm_events) / args.steps
-    engine = {3: "tcgen05 3xFP16, operands pre-split in HBM + cp.async producers", 2: "tcgen05 3xFP16 (scaled hi/lo split)",
+    engine = {4: "tcgen05 3xFP16, persistent, operands pre-split in HBM, staged by cp.async / TMA",
+              3: "tcgen05 3xFP16, operands pre-split in HBM + cp.async producers", 2: "tcgen05 3xFP16 (scaled hi/lo split)",
               1: "tcgen05 3xTF32", 0: "fp32 CUDA-core FMA"}[ops.DEFAULT_PRECISION]
-    kname = {3: "gather_gemm_p16_kernel", 2: "gather_gemm_f16_kernel", 1: "gather_gemm_tc_kernel",
-             0: "gather_gemm_kernel"}[ops.DEFAULT_PRECISION]
+    kname = {4: "gather_gemm_tma_kernel", 3: "gather_gemm_p16_kernel", 2: "gather_gemm_f16_kernel",
+             1: "gather_gemm_tc_kernel", 0: "gather_gemm_kernel"}[ops.DEFAULT_PRECISION]
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
         "frac": achieved / peaks["bf16_tflops"], "traffic": NCU_TRAFFIC_BYTES, "peak_source": peaks["source"],
@@ -343,8 +344,9 @@ def run_ours(args):
         "contraction_share_of_step": all_gemm_ms / (ms / args.steps),
         "whole_step_algorithmic_gbs": (fb + bb) / (ms / args.steps * 1e-3) / 1e9,
         "whole_step_frac_of_hbm_peak": (fb + bb) / (ms / args.steps * 1e-3) / 1e9 / peaks["hbm_gbs"],
-        "note": "dense fp32-accurate contraction (AI ~205 FLOP/B) -> tensor-bound, not HBM-bound; ncu: tensor pipe "
-                "~20% active, L1/shared data pipe ~80% (operand staging of a gathered A) -- see profiles/",
+        "note": "dense fp32-accurate contraction (AI ~205 FLOP/B) -> tensor-bound by the roofline, not HBM-bound; in practice "
+                "paced by the L2->SM gather of the 15x re-read operand (~5.8 TB/s whatever the staging mechanism: LDG+STS, "
+                "cp.async or TMA gather4 -- ablations in profiles/r01b_summary.md); ncu: tensor pipe ~19% active, L2 hit 83%",
     }
 
     cpu = cpu_baseline_leg()

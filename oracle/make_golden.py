@@ -158,22 +158,24 @@ def dump_corr(T, Corr, name, *, n, seed, c, corr_out, out_ch, prev_dim, use_leak
     print(name, "H1", h1, "H2", h2)
 
 
-def dump_model(T, name, *, n, seed):
-    """Full reference HPLFlowNet forward (configs/test_ours_FlyingThings3D.yaml hyper-parameters, evaluate mode)
-    on one pair, CPU, with name-keyed seeded weights (tests/_util.py) -- only inputs and output are stored."""
+def dump_model(T, name, *, n, seed, shallow=False):
+    """Full reference HPLFlowNet (or HPLFlowNetShallow) forward (configs/test_ours_FlyingThings3D.yaml
+    hyper-parameters, evaluate mode; the shallow model on the first five scales) on one pair, CPU, with
+    name-keyed seeded weights (tests/_util.py) -- only inputs and output are stored."""
     import torch
     from torch.utils.data.dataloader import default_collate
     sys.path.insert(0, REPO)
     from hplflownet_b200.synthetic import frustum_pair
-    from tests._util import ModelArgs, name_keyed_init_
+    from tests._util import ModelArgs, ShallowArgs, name_keyed_init_
     from models.HPLFlowNet import HPLFlowNet
-    args = ModelArgs()
+    from models.HPLFlowNet_shallow import HPLFlowNetShallow
+    args = ShallowArgs() if shallow else ModelArgs()
     args.DEVICE = "cpu"
     pc1, pc2 = frustum_pair(n, seed)
-    gen = T.GenerateDataUnsymmetric(_Args(ModelArgs.scales_filter_map))
+    gen = T.GenerateDataUnsymmetric(_Args(args.scales_filter_map))
     p1, p2, sf, gd = gen([pc1.copy(), pc2.copy(), np.zeros_like(pc1)])
     batch = default_collate([(p1, p2, sf, gd, "x")])
-    model = name_keyed_init_(HPLFlowNet(args), seed).eval()
+    model = name_keyed_init_((HPLFlowNetShallow if shallow else HPLFlowNet)(args), seed).eval()
     with torch.no_grad():
         out = model(batch[0], batch[1], batch[3])
     np.savez_compressed(os.path.join(GOLDEN, name), pc1=pc1, pc2=pc2, seed=np.int64(seed), output=out.numpy())
@@ -216,6 +218,7 @@ def main():
 
     # --- caller of the path: full HPLFlowNet forward (BASELINE configs[3] at reduced N) ---
     dump_model(T, "model_frustum256.npz", n=256, seed=3)
+    dump_model(T, "model_shallow_frustum256.npz", n=256, seed=4, shallow=True)
 
     # --- value path: BilateralCorrelationFlex ---
     dump_corr(T, Corr, "corr_prev8.npz", n=160, seed=5, c=8, corr_out=[8, 8], out_ch=[16, 16],

@@ -130,3 +130,9 @@ class ModelArgs:
     DEVICE = "cuda"
     scales_filter_map = [[3., 1, -1, -1], [2., 1, -1, -1], [1., 1, 1, 1], [.5, 1, 1, 1], [.25, 1, 1, 1],
                          [.125, 1, 1, 1], [.0625, 1, 1, 1]]
+
+
+class ShallowArgs(ModelArgs):
+    """HPLFlowNetShallow asserts five scales (models/HPLFlowNet_shallow.py:15); no config in the reference names
+    them, so the first five rows of the FlyingThings3D map are used (rows 2-4 carry the correlation radii)."""
+    scales_filter_map = ModelArgs.scales_filter_map[:5]

@@ -82,3 +82,41 @@ def test_model_backward_matches_float64_oracle():
         assert_close_grad(p.grad, state[name].grad, "grad " + name)
         checked += 1
     assert checked >= 100
+
+
+def test_shallow_model_forward_and_backward():
+    """HPLFlowNetShallow: forward vs the reference model's own output (fixture), gradients vs the
+    oracle in float64."""
+    from hplflownet_b200.HPLFlowNet_shallow import HPLFlowNetShallow
+    from oracle import hplflownet as OM
+    from oracle import lattice as OL
+    from tests._util import ShallowArgs, assert_close_grad
+    g = golden("model_shallow_frustum256.npz")
+    model = name_keyed_init_(HPLFlowNetShallow(ShallowArgs()), int(g["seed"]))
+    state = {k: (v.detach().clone().double().requires_grad_(True) if v.is_floating_point() else v.clone())
+             for k, v in model.state_dict().items()}
+    model = model.cuda().eval()
+    gen = GenerateDataUnsymmetric(ShallowArgs())
+    pc1, pc2, sf, gd = gen([g["pc1"], g["pc2"], g["pc2"] - g["pc1"]])
+    with torch.no_grad():
+        out = model(pc1[None], pc2[None], collate_batch1(gd))
+    assert out.shape == (1, 3, 256)
+    assert_close(out, g["output"], "flow")
+
+    gd_np = OL.generate(g["pc1"], g["pc2"], ShallowArgs.scales_filter_map)
+    gd_ref = [{k: (torch.from_numpy(v)[None] if not isinstance(v, int) else v) for k, v in d.items()} for d in gd_np]
+    gd_ref = [{k: (v.double() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in d.items()} for d in gd_ref]
+    p1, p2 = [torch.from_numpy(np.ascontiguousarray(g[k].T))[None] for k in ("pc1", "pc2")]
+    target = torch.from_numpy(np.ascontiguousarray((g["pc2"] - g["pc1"]).T))[None]
+    loss_ref = torch.norm(OM.forward_shallow(state, p1.double(), p2.double(), gd_ref) - target.double(), p=2, dim=1).mean()
+    loss_ref.backward()
+    model.train()
+    loss = torch.norm(model(pc1[None], pc2[None], collate_batch1(gd)) - sf[None], p=2, dim=1).mean()
+    loss.backward()
+    assert_close(loss.detach(), loss_ref.detach(), "loss")
+    checked = 0
+    for name, p in model.named_parameters():
+        if p.grad is not None:
+            assert_close_grad(p.grad, state[name].grad, "grad " + name)
+            checked += 1
+    assert checked >= 60

@@ -121,3 +121,38 @@ def test_model_oracle_matches_reference_output():
         out = OM.forward(state, pc1, pc2, gd)
     assert out.shape == (1, 3, 256)
     assert_close(out, g["output"], "flow", tol=1e-5)
+
+
+def test_shallow_model_oracle_matches_reference_output():
+    # HPLFlowNetShallow forward: oracle composition vs the reference model's own output
+    from oracle import hplflownet as OM
+    from hplflownet_b200.HPLFlowNet_shallow import HPLFlowNetShallow
+    from tests._util import ShallowArgs, name_keyed_init_
+    g = golden("model_shallow_frustum256.npz")
+    model = name_keyed_init_(HPLFlowNetShallow(ShallowArgs()), int(g["seed"]))
+    state = {k: v.detach() for k, v in model.state_dict().items()}
+    gd = OL.generate(g["pc1"], g["pc2"], ShallowArgs.scales_filter_map)
+    gd = [{k: (torch.from_numpy(v)[None] if not isinstance(v, int) else v) for k, v in d.items()} for d in gd]
+    pc1, pc2 = [torch.from_numpy(np.ascontiguousarray(g[k].T))[None] for k in ("pc1", "pc2")]
+    with torch.no_grad():
+        out = OM.forward_shallow(state, pc1, pc2, gd)
+    assert out.shape == (1, 3, 256)
+    assert_close(out, g["output"], "flow", tol=1e-5)
+
+
+def test_shallow_model_state_dict_layout():
+    # module names / registration order / shapes the reference checkpoint loader relies on (main.py:122, strict=True)
+    from hplflownet_b200.HPLFlowNet_shallow import HPLFlowNetShallow
+    from tests._util import ShallowArgs
+    sd = HPLFlowNetShallow(ShallowArgs()).state_dict()
+    keys = list(sd.keys())
+    assert len(keys) == 90 and keys[0] == "conv1.0.composed_module.0.weight" and keys[-1] == "conv4.bias"
+    assert tuple(sd["bcn1.blur_conv.0.weight"].shape) == (64, 68, 15, 1)            # single bare conv (last_relu=False)
+    assert tuple(sd["bcn1_.blur_conv.0.weight"].shape) == (128, 132, 15, 1)
+    assert tuple(sd["corr2.corr_conv.0.composed_module.0.weight"].shape) == (32, 192, 1, 15, 1)
+    assert tuple(sd["corr1_refine.0.composed_module.0.weight"].shape) == (64, 36, 1)
+    assert tuple(sd["corr3_refine.0.composed_module.0.weight"].shape) == (64, 32, 1)
+    order = [k.split(".")[0] for k in keys]
+    seen = [m for i, m in enumerate(order) if m not in order[:i]]
+    assert seen == ["conv1", "bcn1", "bcn1_", "bcn2", "bcn2_", "bcn3", "bcn3_", "corr1", "corr1_refine", "bcn4", "bcn4_",
+                    "corr2", "corr2_refine", "bcn5", "bcn5_", "corr3", "corr3_refine", "conv2", "conv3", "conv4"]

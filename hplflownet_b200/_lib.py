@@ -32,6 +32,10 @@ SIGNATURES = {
     "hpl_split16": [vp, i64, i64, i64, vp, vp, vp],
     "hpl_blur_gemm_p16": [vp, i64, vp, cint, i64, i64, i64, i64, vp, vp, cint, vp, i64, cint, vp, vp, vp],
     "hpl_blur_wgrad_p16": [vp, i64, vp, cint, i64, i64, i64, i64, vp, vp, vp, vp, vp],
+    "hpl_blur_gemm_f16_amax": [vp, i64, i64, vp, cint, i64, i64, i64, i64, vp, i64, i64, i64, vp, cint, vp, i64, cint, vp, vp, vp, vp],
+    "hpl_normalize_rows_amax": [vp, i64, i64, i64, vp, vp, vp, vp],
+    "hpl_cm_to_rows_amax": [vp, i64, i64, i64, vp, i64, vp, vp],
+    "hpl_act_backward_stats": [vp, i64, vp, i64, i64, i64, cint, vp, vp, vp],
     "hpl_h16_bytes": [i64, i64],
     "hpl_h16_split": [vp, i64, i64, i64, vp, vp, vp],
     "hpl_blur_gemm_tma_workspace": [i64, i64, i64],
@@ -63,7 +67,8 @@ RETURNS_I64 = {"hpl_lattice_table_capacity", "hpl_lattice_scan_blocks", "hpl_blu
 # kernels enqueued per call (for bench.py's gpu_launches claim)
 LAUNCHES = {
     "hpl_scatter_rows": 1, "hpl_normalize_rows": 2, "hpl_gather_rows": 1, "hpl_blur_gemm": 1, "hpl_blur_gemm_tc": 2,
-    "hpl_blur_wgrad": 2, "hpl_blur_wgrad_tc": 2, "hpl_absmax": 1, "hpl_split16": 1, "hpl_h16_split": 1, "hpl_blur_gemm_tma": 3, "hpl_blur_gemm_p16": 3, "hpl_blur_wgrad_p16": 1, "hpl_blur_gemm_f16": 3, "hpl_blur_wgrad_f16": 2, "hpl_act_backward": 1, "hpl_transpose_table": 1, "hpl_cm_to_rows": 1,
+    "hpl_blur_wgrad": 2, "hpl_blur_wgrad_tc": 2, "hpl_absmax": 1, "hpl_blur_gemm_f16_amax": 3, "hpl_normalize_rows_amax": 2, "hpl_cm_to_rows_amax": 1, "hpl_act_backward_stats": 1,
+    "hpl_split16": 1, "hpl_h16_split": 1, "hpl_blur_gemm_tma": 3, "hpl_blur_gemm_p16": 3, "hpl_blur_wgrad_p16": 1, "hpl_blur_gemm_f16": 3, "hpl_blur_wgrad_f16": 2, "hpl_act_backward": 1, "hpl_transpose_table": 1, "hpl_cm_to_rows": 1,
     "hpl_rows_to_cm": 1, "hpl_channel_sums": 1, "hpl_fill_zero": 1, "hpl_fill_i32": 1,
     "hpl_corr_gather": 1, "hpl_corr_scatter": 1, "hpl_column_sums": 1,
     "hpl_lattice_init_range": 1, "hpl_lattice_points": 1, "hpl_lattice_insert": 6,

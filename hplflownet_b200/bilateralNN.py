@@ -68,8 +68,9 @@ def conv2d_layers(module_list, use_leaky):
 
 
 def kernel_weight(w):
-    """(Co, C, F, 1) conv weight -> (F, C, Co) contiguous operand of hpl_blur_gemm."""
-    return w.detach().reshape(w.size(0), w.size(1), -1).permute(2, 1, 0).contiguous()
+    """(Co, C, F, 1) conv weight -> its (F, C, Co) VIEW, the operand of the gather-GEMM (engine 2 reads it strided;
+    ops.blur_gemm makes a contiguous copy for the engines that need one)."""
+    return w.detach().reshape(w.size(0), w.size(1), -1).permute(2, 1, 0)
 
 
 def conv_weight_grad(dw, like):
@@ -88,23 +89,30 @@ class _BCLFunction(torch.autograd.Function):
         nbr2 = nbr[0].contiguous()                           # (F, H)
         h = nbr2.size(1)
         inv, fuse_norm = None, False
+        # engine 2: the producer of the lattice rows records max|rows| itself (no separate absmax pass)
+        lat_amax = ops.amax_slots(feat.device, 1) if (ops.fused_stats() and c_in % 4 == 0) else None
         if do_splat:
             bary_i, off_i = in_bary[0].contiguous(), in_off[0].contiguous()
             lat, wsum = ops.scatter_rows(feat, bary_i, off_i, h, use_norm)
+            if not use_norm:
+                lat_amax = None
             if use_norm:
                 # The contraction kernels can also apply 1/(wsum+1e-5) while gathering (row_scale), saving
                 # this pass; measured on B200 the extra dependent load costs the forward GEMM more (+70 us
                 # per 32 clouds) than the 25 us pass it removes, so it is off by default.
                 fuse_norm = FUSE_NORMALISATION and ops.tc_path(c_in)
-                inv = ops.reciprocal_(wsum) if fuse_norm else ops.normalize_rows_(lat, c_in, wsum)
+                if fuse_norm:
+                    inv, lat_amax = ops.reciprocal_(wsum), None
+                else:
+                    inv = ops.normalize_rows_(lat, c_in, wsum, amax=lat_amax)
         else:
             bary_i = off_i = None
-            lat = ops.cm_to_rows(feat)
+            lat = ops.cm_to_rows(feat, amax=lat_amax)
 
         layers = [(kernel_weight(params[2 * l]), params[2 * l + 1].detach(), acts[l]) for l in range(len(acts))]
         scale0 = inv if (do_splat and use_norm and fuse_norm) else None
         xs, chans, out_cm = _stack.forward(lat, c_in, h, layers, nbr2, last_channel_major=not do_slice,
-                                           first_row_scale=scale0)
+                                           first_row_scale=scale0, x_amax=lat_amax)
 
         if do_slice:
             bary_o, off_o = out_bary[0].contiguous(), out_off[0].contiguous()

@@ -105,7 +105,8 @@ __global__ void absmax_tail_kernel(const float* __restrict__ x, long long lo, lo
 // ------------------------------------------------------------------------------ weight image
 // w (F, C, Co) fp32 -> per (N tile, K block of 32) [hi 4 KB | lo 4 KB] in the shared-memory layout.
 template <int TNv>
-__global__ void weight_image16_kernel(const float* __restrict__ w, int filter_size, int c_in, int c_out, int kb_per_tap,
+__global__ void weight_image16_kernel(const float* __restrict__ w, long long w_sf, long long w_sc, long long w_so,
+                                      int filter_size, int c_in, int c_out, int kb_per_tap,
                                       const uint32_t* __restrict__ w_amax, uint8_t* __restrict__ image) {
     constexpr int TN = TNv;
     constexpr int kBHalf = TN * TK * 2;
@@ -126,7 +127,7 @@ __global__ void weight_image16_kernel(const float* __restrict__ w, int filter_si
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = c0 + 8 * kc + i;
-        v[i] = (c < c_in && o < c_out) ? __ldg(w + ((long long)f * c_in + c) * c_out + o) : 0.f;
+        v[i] = (c < c_in && o < c_out) ? __ldg(w + f * w_sf + c * w_sc + o * w_so) : 0.f;
     }
     uint32_t hi[4], lo[4];
     split8(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]), inv_s, hi, lo);
@@ -142,7 +143,7 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
                        int filter_size, long long n_out_rows, int c_in, int c_out, int kb_per_tap,
                        const uint8_t* __restrict__ w_image, const float* __restrict__ bias, int act, float* __restrict__ out,
                        long long ld_out, int out_cm, int n_main, const uint32_t* __restrict__ in_amax,
-                       const uint32_t* __restrict__ w_amax) {
+                       const uint32_t* __restrict__ w_amax, uint32_t* __restrict__ out_amax) {
     // tile width (64 for narrow layers, 128 for Co >= 128: half as many re-gathers of A) and ring depth
     constexpr int TN = TNv, kStages = kStagesV;
     constexpr int kBHalf = TN * TK * 2;
@@ -298,6 +299,7 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
         const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
         const int o0 = n_tile * TN;
         const float s_ab = s_in * s_w;
+        float y_max = 0.f;                                                  // max |output| of this thread's row
 #pragma unroll 1
         for (int cb = 0; cb < TN; cb += 16) {
             float sum[16];
@@ -317,6 +319,7 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
                     const int o = o0 + cb + j;
                     const float b = (bias != nullptr && o < c_out) ? __ldg(bias + o) : 0.f;
                     y[j] = apply_act(fmaf(sum[j], s_ab, b), act);
+                    if (o < c_out) y_max = fmaxf(y_max, fabsf(y[j]));
                 }
                 if (!out_cm) {
                     float* p = out + m * ld_out + o0 + cb;
@@ -602,6 +605,15 @@ int64_t hpl_blur_gemm_f16_workspace(int64_t filter_size, int64_t c_in, int64_t c
 int hpl_blur_gemm_f16(const float* in, int64_t ld_in, int64_t n_in_rows, const void* nbr, int idx64, int64_t filter_size,
                       int64_t n_out_rows, int64_t c_in, int64_t c_out, const float* w, const float* bias, int act, float* out,
                       int64_t ld_out, int out_channel_major, void* workspace, const uint32_t* in_amax, void* stream) {
+    return hpl_blur_gemm_f16_amax(in, ld_in, n_in_rows, nbr, idx64, filter_size, n_out_rows, c_in, c_out, w, 0, 0, 0, bias, act, out,
+                                  ld_out, out_channel_major, workspace, in_amax, nullptr, stream);
+}
+
+int hpl_blur_gemm_f16_amax(const float* in, int64_t ld_in, int64_t n_in_rows, const void* nbr, int idx64, int64_t filter_size,
+                           int64_t n_out_rows, int64_t c_in, int64_t c_out, const float* w, int64_t w_sf, int64_t w_sc, int64_t w_so,
+                           const float* bias, int act, float* out, int64_t ld_out, int out_channel_major, void* workspace,
+                           const uint32_t* in_amax, uint32_t* out_amax, void* stream) {
+    if (w_sf == 0 && w_sc == 0 && w_so == 0) { w_sf = c_in * c_out; w_sc = c_out; w_so = 1; }   // contiguous (F, C, Co)
     HPL_CHECK_ARG(in && w && out && workspace && in_amax && c_in > 0 && c_out > 0 && filter_size > 0 && c_in % 4 == 0);
     HPL_CHECK_ARG(ld_in % 4 == 0 && ld_in >= c_in && ((uintptr_t)in & 15) == 0 && ((uintptr_t)workspace & 15) == 0);
     HPL_CHECK_ARG(((uintptr_t)w & 15) == 0);
@@ -622,9 +634,9 @@ int hpl_blur_gemm_f16(const float* in, int64_t ld_in, int64_t n_in_rows, const v
     if (rc != 0) return rc;
     const long long chunks = n_tiles * filter_size * kb_per_tap * (tn * (TK / 8));
     if (wide)
-        weight_image16_kernel<128><<<(unsigned)((chunks + 255) / 256), 256, 0, s>>>(w, (int)filter_size, (int)c_in, (int)c_out, kb_per_tap, w_amax, image);
+        weight_image16_kernel<128><<<(unsigned)((chunks + 255) / 256), 256, 0, s>>>(w, w_sf, w_sc, w_so, (int)filter_size, (int)c_in, (int)c_out, kb_per_tap, w_amax, image);
     else
-        weight_image16_kernel<64><<<(unsigned)((chunks + 255) / 256), 256, 0, s>>>(w, (int)filter_size, (int)c_in, (int)c_out, kb_per_tap, w_amax, image);
+        weight_image16_kernel<64><<<(unsigned)((chunks + 255) / 256), 256, 0, s>>>(w, w_sf, w_sc, w_so, (int)filter_size, (int)c_in, (int)c_out, kb_per_tap, w_amax, image);
     const long long steps = (long long)filter_size * kb_per_tap * (TK / 16);
     // accumulate steps per hi.hi accumulator <= ~160-190; TMEM holds (n_main + 1) * tn <= 512 columns
     const int n_main = steps <= 160 ? 1 : ((steps <= 480 || wide) ? 3 : 7);
@@ -632,7 +644,7 @@ int hpl_blur_gemm_f16(const float* in, int64_t ld_in, int64_t n_in_rows, const v
 #define HPL_LAUNCH_F16(I64, TNV, ST)                                                                                         \
     gather_gemm_f16_kernel<I64, TNV, ST><<<grid, kThreads, ST * (2 * kAHalf + 2 * TNV * TK * 2) + 1024, s>>>(                \
         in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, (int)c_in, (int)c_out, kb_per_tap, image, bias, act, out,   \
-        ld_out, out_channel_major, n_main, in_amax, w_amax)
+        ld_out, out_channel_major, n_main, in_amax, w_amax, out_amax)
     if (wide) {
         if (idx64) HPL_LAUNCH_F16(true, 128, 3); else HPL_LAUNCH_F16(false, 128, 3);
     } else {

@@ -137,21 +137,40 @@ gather_rows_kernel(const float* __restrict__ rows, long long ld, const float* __
 }
 
 // ------------------------------------------------------------------------------ normalise
+// max |x| of a block -> one RED.MAX on the device scalar (non-negative floats order as unsigned integers)
+__device__ __forceinline__ void block_absmax_to(float m, uint32_t* out) {
+    __shared__ float warp_max[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+    if ((tid & 31) == 0) warp_max[tid >> 5] = m;
+    __syncthreads();
+    if (tid == 0) {
+        const int n_warps = (blockDim.x * blockDim.y + 31) >> 5;
+        for (int w = 1; w < n_warps; ++w) m = fmaxf(m, warp_max[w]);
+        if (m > 0.f) atomicMax(out, __float_as_uint(m));
+    }
+}
+
 __global__ void normalize_rows_kernel(float* __restrict__ rows, long long ld, long long n_rows, int quads,
-                                      const float* __restrict__ wsum, float* __restrict__ inv) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_rows * quads) return;
-    const long long v = t / quads;
-    const int q = (int)(t - v * quads);
-    const float s = 1.0f / (wsum[v] + 1e-5f);   // bilateralNN.py:185
-    float4* p = reinterpret_cast<float4*>(rows + v * ld) + q;
-    float4 a = *p;
-    a.x *= s; a.y *= s; a.z *= s; a.w *= s;
-    *p = a;
-    // every quad-thread of a row read wsum[v] before any of them can have written inv[v] only
-    // if inv does not alias wsum; when it does, the q == quads-1 thread may race with readers.
-    // So the in-place case is handled by writing inv in a second kernel (see launcher).
-    if (inv != nullptr && q == 0 && inv != wsum) inv[v] = s;
+                                      const float* __restrict__ wsum, float* __restrict__ inv, uint32_t* __restrict__ amax) {
+    float m = 0.f;
+    const long long total = n_rows * quads;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long v = t / quads;
+        const int q = (int)(t - v * quads);
+        const float s = 1.0f / (wsum[v] + 1e-5f);   // bilateralNN.py:185
+        float4* p = reinterpret_cast<float4*>(rows + v * ld) + q;
+        float4 a = *p;
+        a.x *= s; a.y *= s; a.z *= s; a.w *= s;
+        *p = a;
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+        // every quad-thread of a row read wsum[v] before any of them can have written inv[v] only
+        // if inv does not alias wsum; when it does, the q == quads-1 thread may race with readers.
+        // So the in-place case is handled by writing inv in a second kernel (see launcher).
+        if (inv != nullptr && q == 0 && inv != wsum) inv[v] = s;
+    }
+    if (amax != nullptr) block_absmax_to(m, amax);          // fused hpl_absmax of the normalised rows (pads are 0)
 }
 __global__ void reciprocal_kernel(float* __restrict__ w, long long n) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -175,19 +194,57 @@ __global__ void act_backward_kernel(float* __restrict__ dz, long long ld_dz, con
     *pd = d;
 }
 
+// One pass over dz (n_rows, ld): dz *= act'(y) (skipped when y == nullptr), max|dz| -> amax, sum_v dz[v, :] -> colsum.
+// Replaces act_backward + hpl_absmax + hpl_column_sums (three passes over the same 4 * H * Co bytes) in the backward of
+// every convolution layer.  Block = 64 columns x 4 row lanes over a slab of rows.
+template <bool HAS_Y>
+__global__ void __launch_bounds__(256)
+act_backward_stats_kernel(float* __restrict__ dz, long long ld_dz, const float* __restrict__ y, long long ld_y,
+                          long long n_rows, int channels, float slope, long long rows_per_block,
+                          uint32_t* __restrict__ amax, float* __restrict__ colsum) {
+    __shared__ float part[4][64];
+    const int col = threadIdx.x & 63, lane_r = threadIdx.x >> 6;
+    const int o = blockIdx.x * 64 + col;
+    const long long lo = rows_per_block * blockIdx.y, hi = min(n_rows, lo + rows_per_block);
+    float acc = 0.f, m = 0.f;
+    if (o < channels) {
+        for (long long v = lo + lane_r; v < hi; v += 4) {
+            float d = dz[v * ld_dz + o];
+            if (HAS_Y) {
+                d *= __ldg(y + v * ld_y + o) > 0.f ? 1.f : slope;
+                dz[v * ld_dz + o] = d;
+            }
+            acc += d;
+            m = fmaxf(m, fabsf(d));
+        }
+    }
+    part[lane_r][col] = acc;
+    __syncthreads();
+    if (colsum != nullptr && lane_r == 0 && o < channels && lo < hi)
+        atomicAdd(colsum + o, (part[0][col] + part[1][col]) + (part[2][col] + part[3][col]));
+    if (amax != nullptr) block_absmax_to(m, amax);
+}
+
 // ------------------------------------------------------------------------------ transposes
 // cm (C, ld_cm) -> rows (n, ld); pad columns [C, ld) of rows are written as zeros.
 __global__ void cm_to_rows_kernel(const float* __restrict__ cm, long long ld_cm, long long n, int channels,
-                                  float* __restrict__ rows, long long ld) {
+                                  float* __restrict__ rows, long long ld, uint32_t* __restrict__ amax) {
     __shared__ float tile[32][33];
     const long long v0 = (long long)blockIdx.x * 32;
     const int c0 = blockIdx.y * 32;
+    float m = 0.f;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const int c = c0 + i;
         const long long v = v0 + threadIdx.x;
-        tile[i][threadIdx.x] = (c < channels && v < n) ? __ldg(cm + (long long)c * ld_cm + v) : 0.f;
+        const float x = (c < channels && v < n) ? __ldg(cm + (long long)c * ld_cm + v) : 0.f;
+        tile[i][threadIdx.x] = x;
+        m = fmaxf(m, fabsf(x));
     }
-    __syncthreads();
+    if (amax != nullptr) {
+        block_absmax_to(m, amax);                            // (contains the __syncthreads the tile needs)
+    } else {
+        __syncthreads();
+    }
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const long long v = v0 + i;
         const int c = c0 + threadIdx.x;
@@ -279,6 +336,11 @@ int hpl_scatter_rows(const float* x, const float* bary, const void* off, int idx
 
 int hpl_normalize_rows(float* rows, int64_t ld, int64_t n_rows, int64_t channels, const float* wsum,
                        float* inv, void* stream) {
+    return hpl_normalize_rows_amax(rows, ld, n_rows, channels, wsum, inv, nullptr, stream);
+}
+
+int hpl_normalize_rows_amax(float* rows, int64_t ld, int64_t n_rows, int64_t channels, const float* wsum,
+                            float* inv, uint32_t* amax, void* stream) {
     HPL_CHECK_ARG(wsum);
     if (n_rows == 0) return 0;
     if (rows == nullptr) {   // reciprocal only
@@ -288,7 +350,9 @@ int hpl_normalize_rows(float* rows, int64_t ld, int64_t n_rows, int64_t channels
     }
     HPL_CHECK_ARG(ld % 4 == 0 && ld >= channels && ((uintptr_t)rows & 15) == 0);
     const int quads = (int)((channels + 3) / 4);
-    normalize_rows_kernel<<<blocks_for(n_rows * quads, 256), 256, 0, as_stream(stream)>>>(rows, ld, n_rows, quads, wsum, inv);
+    unsigned blocks = blocks_for(n_rows * quads, 256);
+    if (blocks > 16u * num_sms()) blocks = 16u * num_sms();            // grid-stride: one RED.MAX per block
+    normalize_rows_kernel<<<blocks, 256, 0, as_stream(stream)>>>(rows, ld, n_rows, quads, wsum, inv, amax);
     if (inv != nullptr && inv == wsum)
         reciprocal_kernel<<<blocks_for(n_rows, 256), 256, 0, as_stream(stream)>>>(inv, n_rows);
     HPL_RETURN_LAST();
@@ -318,6 +382,22 @@ int hpl_act_backward(float* dz, int64_t ld_dz, const float* y, int64_t ld_y, int
     HPL_RETURN_LAST();
 }
 
+int hpl_act_backward_stats(float* dz, int64_t ld_dz, const float* y, int64_t ld_y, int64_t n_rows, int64_t channels,
+                           int act, uint32_t* amax, float* colsum, void* stream) {
+    HPL_CHECK_ARG(dz && ld_dz >= channels && channels > 0 && (act == HPL_ACT_NONE || (y && ld_y >= channels)));
+    if (n_rows == 0) return 0;
+    long long blocks_y = (n_rows + 127) / 128;
+    if (blocks_y > 2048) blocks_y = 2048;
+    const long long rpb = (n_rows + blocks_y - 1) / blocks_y;
+    dim3 grid((unsigned)((channels + 63) / 64), (unsigned)blocks_y);
+    const float slope = act == HPL_ACT_LEAKY ? HPL_LEAKY_RATE : 0.f;
+    if (act == HPL_ACT_NONE)
+        act_backward_stats_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(dz, ld_dz, nullptr, 0, n_rows, (int)channels, 1.f, rpb, amax, colsum);
+    else
+        act_backward_stats_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(dz, ld_dz, y, ld_y, n_rows, (int)channels, slope, rpb, amax, colsum);
+    HPL_RETURN_LAST();
+}
+
 int hpl_transpose_table(const void* tbl, int idx64, int64_t filter_size, int64_t n_rows, int32_t* tbl_t,
                         int64_t n_src_rows, int32_t* collisions, void* stream) {
     HPL_CHECK_ARG(tbl && tbl_t && filter_size > 0);
@@ -332,10 +412,15 @@ int hpl_transpose_table(const void* tbl, int idx64, int64_t filter_size, int64_t
 
 int hpl_cm_to_rows(const float* cm, int64_t ld_cm, int64_t n, int64_t channels, float* rows, int64_t ld,
                    void* stream) {
+    return hpl_cm_to_rows_amax(cm, ld_cm, n, channels, rows, ld, nullptr, stream);
+}
+
+int hpl_cm_to_rows_amax(const float* cm, int64_t ld_cm, int64_t n, int64_t channels, float* rows, int64_t ld,
+                        uint32_t* amax, void* stream) {
     HPL_CHECK_ARG(cm && rows && ld >= channels && ld_cm >= n);
     if (n == 0) return 0;
     dim3 grid(blocks_for(n, 32), blocks_for(ld, 32)), block(32, 8);
-    cm_to_rows_kernel<<<grid, block, 0, as_stream(stream)>>>(cm, ld_cm, n, (int)channels, rows, ld);
+    cm_to_rows_kernel<<<grid, block, 0, as_stream(stream)>>>(cm, ld_cm, n, (int)channels, rows, ld, amax);
     HPL_RETURN_LAST();
 }
 

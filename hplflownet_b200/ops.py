@@ -93,10 +93,25 @@ def scatter_rows(x, bary, off, n_rows, want_wsum):
     return rows, wsum
 
 
-def normalize_rows_(rows, channels, wsum):
-    """In place: rows *= 1/(wsum+1e-5); wsum becomes the reciprocal (returned)."""
-    _lib.call("hpl_normalize_rows", rows.data_ptr(), rows.stride(0), rows.size(0), channels,
-              wsum.data_ptr(), wsum.data_ptr(), _stream())
+def amax_slots(device, n):
+    """n zeroed device scalars for the fused max|x| statistics (kernels RED.MAX into them); index with [i:i+1]."""
+    return torch.zeros(n, dtype=torch.int32, device=device)
+
+
+def fused_stats():
+    """True when the default engine takes its operand scales from producer-fused statistics (engine 2)."""
+    return DEFAULT_PRECISION == 2
+
+
+def normalize_rows_(rows, channels, wsum, amax=None):
+    """In place: rows *= 1/(wsum+1e-5); wsum becomes the reciprocal (returned).  amax: zeroed slot that receives
+    max|rows| of the result (saves the separate hpl_absmax pass)."""
+    if amax is not None:
+        _lib.call("hpl_normalize_rows_amax", rows.data_ptr(), rows.stride(0), rows.size(0), channels,
+                  wsum.data_ptr(), wsum.data_ptr(), amax.data_ptr(), _stream())
+    else:
+        _lib.call("hpl_normalize_rows", rows.data_ptr(), rows.stride(0), rows.size(0), channels,
+                  wsum.data_ptr(), wsum.data_ptr(), _stream())
     return wsum
 
 
@@ -132,6 +147,22 @@ def h16_split(x, channels, amax):
     return buf
 
 
+def _dense_permutation(w):
+    """True when the 3-D tensor w covers one dense buffer of w.numel() elements exactly once (a permuted view of a
+    contiguous tensor, possibly with broadcast-free size-1 dims) starting at its own data pointer."""
+    dims = sorted(((st, sz) for st, sz in zip(w.stride(), w.shape) if sz > 1))
+    expect = 1
+    for st, sz in dims:
+        if st != expect:
+            return False
+        expect *= sz
+    return True
+
+
+def _base_ptr(w):
+    return w.data_ptr()
+
+
 def tc_path(c_in, precision=None):
     """True when the tensor-core kernels (which can fold ``row_scale``) will run for this operand."""
     return (DEFAULT_PRECISION if precision is None else precision) >= 1 and c_in % 4 == 0
@@ -150,9 +181,13 @@ def gather_rows(rows, channels, bary, off, scale=None, bias=None):
 
 
 def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_major=False, precision=None,
-              tag="fwd", row_scale=None, x_amax=None, x16=None):
-    """out[v] = act(bias + sum_f x[nbr[f, v]] @ w[f]);  w (F, C, Co)."""
-    _f32(x, "x"); _f32(w, "w")
+              tag="fwd", row_scale=None, x_amax=None, x16=None, out_amax=None):
+    """out[v] = act(bias + sum_f x[nbr[f, v]] @ w[f]);  w (F, C, Co) -- any dense permutation of a contiguous buffer
+    (e.g. a view of the conv weight): engine 2 reads it strided, the other engines get a contiguous copy.
+    out_amax: zeroed slot that receives max|out|."""
+    _f32(x, "x")
+    if not (w.is_cuda and w.dtype == torch.float32):
+        raise ValueError("w must be a CUDA float32 tensor")
     f, c, co = w.shape
     assert c == c_in
     if nbr is not None:
@@ -176,6 +211,8 @@ def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_majo
         precision = 1
     if precision == 1 and c % 4 != 0:
         precision = 0
+    if precision != 2:
+        w = w.contiguous()
     if precision == 4:
         ws = _workspace(x.device, _lib.load().hpl_blur_gemm_tma_workspace(f, c, co))
         if x16 is None:
@@ -198,10 +235,14 @@ def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_majo
         ws = _workspace(x.device, _lib.load().hpl_blur_gemm_f16_workspace(f, c, co))
         if x_amax is None:
             x_amax = absmax(x)
+        if not _dense_permutation(w):
+            w = w.contiguous()
         with _timed(tag):
-            _lib.call("hpl_blur_gemm_f16", x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, f, n_out_rows, c, co,
-                      w.data_ptr(), bias_ptr, act, out.data_ptr(), out.stride(0), int(out_channel_major),
-                      ws.data_ptr(), x_amax.data_ptr(), _stream())
+            _lib.call("hpl_blur_gemm_f16_amax", x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, f, n_out_rows, c, co,
+                      _base_ptr(w), w.stride(0), w.stride(1), w.stride(2),
+                      bias_ptr, act, out.data_ptr(), out.stride(0), int(out_channel_major),
+                      ws.data_ptr(), x_amax.data_ptr(), out_amax.data_ptr() if out_amax is not None else None, _stream())
+        out_amax = None
     elif precision == 1:
         ws = _workspace(x.device, _lib.load().hpl_blur_gemm_tc_workspace(f, c, co))
         with _timed(tag):
@@ -214,6 +255,8 @@ def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_majo
             _lib.call("hpl_blur_gemm", x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, f, n_out_rows, c, co,
                       w.data_ptr(), bias_ptr, act, out.data_ptr(), out.stride(0), int(out_channel_major), 0,
                       _stream())
+    if out_amax is not None:                 # an engine without the fused epilogue statistic ran
+        _lib.call("hpl_absmax", out.data_ptr(), out.numel(), out_amax.data_ptr(), _stream())
     return out
 
 
@@ -268,6 +311,14 @@ def blur_wgrad(x, c_in, nbr, n_out_rows, dz, c_out, filter_size, want_db=True, p
     return dw, db
 
 
+def act_backward_stats_(dz, y, channels, act, amax=None, colsum=None):
+    """One pass: dz *= act'(y) in place, max|dz| -> amax (zeroed slot), column sums of dz += colsum (zeroed (Co,))."""
+    _lib.call("hpl_act_backward_stats", dz.data_ptr(), dz.stride(0), y.data_ptr() if act != ACT_NONE else None,
+              y.stride(0) if act != ACT_NONE else 0, dz.size(0), channels, act,
+              amax.data_ptr() if amax is not None else None, colsum.data_ptr() if colsum is not None else None, _stream())
+    return dz
+
+
 def act_backward_(dz, y, channels, act):
     if act != ACT_NONE:
         _lib.call("hpl_act_backward", dz.data_ptr(), dz.stride(0), y.data_ptr(), y.stride(0), dz.size(0),
@@ -285,12 +336,16 @@ def transpose_table(tbl, n_src_rows):
     return out
 
 
-def cm_to_rows(cm):
-    """(C, n) channel-major -> (n, ld) vertex-major."""
+def cm_to_rows(cm, amax=None):
+    """(C, n) channel-major -> (n, ld) vertex-major.  amax: zeroed slot that receives max|cm|."""
     _f32(cm, "cm")
     c, n = cm.shape
     rows = torch.empty((n, round4(c)), dtype=torch.float32, device=cm.device)
-    _lib.call("hpl_cm_to_rows", cm.data_ptr(), cm.stride(0), n, c, rows.data_ptr(), rows.stride(0), _stream())
+    if amax is not None:
+        _lib.call("hpl_cm_to_rows_amax", cm.data_ptr(), cm.stride(0), n, c, rows.data_ptr(), rows.stride(0),
+                  amax.data_ptr(), _stream())
+    else:
+        _lib.call("hpl_cm_to_rows", cm.data_ptr(), cm.stride(0), n, c, rows.data_ptr(), rows.stride(0), _stream())
     return rows
 
 

@@ -17,10 +17,12 @@ from .module_utils import Conv1dReLU
 class _PointwiseFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, acts, x, *params):
-        xr = ops.cm_to_rows(x[0].contiguous())
-        n, c_in = xr.size(0), x.size(1)
+        c_in = x.size(1)
+        x_amax = ops.amax_slots(x.device, 1) if (ops.fused_stats() and c_in % 4 == 0) else None
+        xr = ops.cm_to_rows(x[0].contiguous(), amax=x_amax)
+        n = xr.size(0)
         layers = [(kernel_weight(params[2 * l]), params[2 * l + 1].detach(), acts[l]) for l in range(len(acts))]
-        xs, chans, out_cm = _stack.forward(xr, c_in, n, layers, None, last_channel_major=True)
+        xs, chans, out_cm = _stack.forward(xr, c_in, n, layers, None, last_channel_major=True, x_amax=x_amax)
         out = out_cm if out_cm is not None else ops.rows_to_cm(xs[-1], chans[-1])
         ctx.xs, ctx.chans, ctx.layers, ctx.n = xs, chans, layers, n
         ctx.amaxs = _stack.forward.last_amaxs

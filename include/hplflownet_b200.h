@@ -153,6 +153,28 @@ int hpl_blur_wgrad_p16(const void* in16, int64_t n_in_rows, const void* nbr, int
                        const void* dz16, float* dw, const uint32_t* in_amax, const uint32_t* dz_amax,
                        void* stream);
 
+/* Fused statistics (one pass instead of three over the same rows).  `amax` slots are device scalars holding the
+ * bit pattern of max|x| (as hpl_absmax writes it); the caller zeroes them, the kernels RED.MAX into them.
+ *   hpl_blur_gemm_f16_amax: hpl_blur_gemm_f16 whose epilogue also records max|out| (post-activation) in `out_amax`
+ *     -- the 3xFP16 scale of the next layer's input (NULL = off) -- and whose weight operand is STRIDED: element
+ *     (f, c, o) of the logical (F, C, Co) weight sits at w[f * w_sf + c * w_sc + o * w_so] inside one dense buffer of
+ *     F * C * Co floats starting at w, so the reference's (Co, C, F, 1) conv weight (strides 1, F, C * F) and its
+ *     transpose for the data gradient are consumed in place, without permuted copies.  All three 0 = contiguous.
+ *   hpl_normalize_rows_amax / hpl_cm_to_rows_amax: the same for the producers of a stack's first input.
+ *   hpl_act_backward_stats: dz *= act'(y) (act NONE: dz untouched, y may be NULL), max|dz| -> amax, sum_v dz[v, :] ->
+ *     colsum (+=, the convolution's bias gradient); amax / colsum may be NULL. */
+int hpl_blur_gemm_f16_amax(const float* in, int64_t ld_in, int64_t n_in_rows, const void* nbr, int idx64,
+                           int64_t filter_size, int64_t n_out_rows, int64_t c_in, int64_t c_out,
+                           const float* w, int64_t w_sf, int64_t w_sc, int64_t w_so, const float* bias, int act,
+                           float* out, int64_t ld_out, int out_channel_major, void* workspace,
+                           const uint32_t* in_amax, uint32_t* out_amax, void* stream);
+int hpl_normalize_rows_amax(float* rows, int64_t ld, int64_t n_rows, int64_t channels, const float* wsum,
+                            float* inv, uint32_t* amax, void* stream);
+int hpl_cm_to_rows_amax(const float* cm, int64_t ld_cm, int64_t n, int64_t channels, float* rows, int64_t ld,
+                        uint32_t* amax, void* stream);
+int hpl_act_backward_stats(float* dz, int64_t ld_dz, const float* y, int64_t ld_y, int64_t n_rows,
+                           int64_t channels, int act, uint32_t* amax, float* colsum, void* stream);
+
 /* TMA-gathered variant (csrc/gemm_tma.cu): same contraction as hpl_blur_gemm_f16 (replaces the advanced-index
  * gather + Conv2d of models/bilateralNN.py:198-221), but the gathered operand is moved by the Tensor Memory
  * Accelerator (cp.async.bulk.tensor ... tile::gather4, four lattice rows per instruction, written straight into

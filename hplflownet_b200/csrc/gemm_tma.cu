@@ -31,10 +31,12 @@
 //     number of issuing warps: ~3 TB/s over the chip, below the ~5.8 TB/s the LSU paths reach on the same rows.
 //   * cp.async alone: 0.25 ms -- on par with the register-staged engine 2 (0.25 ms in the same harness), hybrids no
 //     better.  Ablations (loads off / MMAs off / both): every variant of the L2 -> SM gather tops out near 5.8-5.9 TB/s
-//     (ncu: L2 13 % busy, L1 19 %, tensor pipe 14 %, nothing saturated): the pattern, not the staging mechanism, is the
-//     limit, so the next step is fewer L2 -> SM bytes (vertex re-ordering for shared-memory reuse across taps), see
-//     DESIGN.md.  Pitfalls found on the way: a per-tap dependent index load cost 150 us (hence the shared-memory index
-//     block), a 64-bit division per K step in the issuer thread another 40 us.
+//     (ncu: L2 13 % busy, L1 19 %, tensor pipe 14 %, nothing saturated).  It is not a byte limit either: spatially
+//     sorted vertices (overlapping gathers) change nothing for engine 2 and slow this engine down (tools/try_sorted.py).
+//     Engine 2 is bound by its producers' instruction stream, this engine by its ONE MMA-issuing thread and ONE ring per
+//     SM (~2000 cycles per stage); the next step is two issue pipelines per SM, see DESIGN.md 3.2b.  Pitfalls found on
+//     the way: a per-tap dependent index load cost 150 us (hence the shared-memory index block), a 64-bit division per K
+//     step in the issuer thread another 40 us.
 //   * Since engine 4 needs two extra split passes (21 us each) per layer and direction, engine 2 stays the default.
 //
 // h16 image of a vertex-major fp32 matrix x (n_rows, C):  (n_rows + 1) rows of [ hi(ld16) | lo(ld16) ] halves,

@@ -24,6 +24,7 @@
 // with 8-byte STS; the chunk strides (LBO / SBO, free parameters of the UMMA descriptor) are padded by 32
 // bytes so that the 4 chunks a half warp touches fall into 4 different bank groups (conflict-free).
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "tc_common.cuh"
 
@@ -137,15 +138,19 @@ __global__ void weight_image16_kernel(const float* __restrict__ w, long long w_s
 }
 
 // ------------------------------------------------------------------------------ forward / dgrad
-template <bool I64, int TNv, int kStagesV>
-__global__ void __launch_bounds__(kThreads, 2)
+// PW producer warps (8: two CTAs per SM; 16: the 256-wide tile, one CTA per SM).  kb_per_split > 0: the K blocks are
+// split over blockIdx.z, every CTA accumulates its range and adds its partial tile to `out` with fp32 RED (out zeroed
+// by the launcher, bias / activation applied by bias_act_kernel afterwards).
+template <bool I64, int TNv, int kStagesV, int PW>
+__global__ void __launch_bounds__(PW * 32 + 64, PW == 8 ? 2 : 1)
 gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_rows, const void* __restrict__ nbr,
                        int filter_size, long long n_out_rows, int c_in, int c_out, int kb_per_tap,
                        const uint8_t* __restrict__ w_image, const float* __restrict__ bias, int act, float* __restrict__ out,
                        long long ld_out, int out_cm, int n_main, const uint32_t* __restrict__ in_amax,
-                       const uint32_t* __restrict__ w_amax, uint32_t* __restrict__ out_amax) {
-    // tile width (64 for narrow layers, 128 for Co >= 128: half as many re-gathers of A) and ring depth
+                       const uint32_t* __restrict__ w_amax, uint32_t* __restrict__ out_amax, int kb_per_split) {
+    // tile width (64 for narrow layers, 128 for Co >= 128, 256 for Co >= 256: fewer re-gathers of A) and ring depth
     constexpr int TN = TNv, kStages = kStagesV;
+    constexpr int kProducerWarps = PW, kRowsPerWarp = TM / PW, NB = kRowsPerWarp / 4;
     constexpr int kBHalf = TN * TK * 2;
     constexpr int kStageBytes = 2 * kAHalf + 2 * kBHalf;
     constexpr uint32_t kB_LBO = TN * 16;
@@ -158,7 +163,10 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long m0 = (long long)blockIdx.x * TM;
     const int n_tile = blockIdx.y;
-    const int n_kb = filter_size * kb_per_tap;
+    const int n_kb_total = filter_size * kb_per_tap;
+    const int kb_lo = kb_per_split > 0 ? (int)blockIdx.z * kb_per_split : 0;
+    const int n_kb = kb_per_split > 0 ? min(kb_per_split, n_kb_total - kb_lo) : n_kb_total;      // K blocks of this CTA
+    const bool partial = kb_per_split > 0;
     const uint32_t tmem_cols = (uint32_t)(TN * (n_main + 1));
 
     if (threadIdx.x == 0) {
@@ -184,38 +192,41 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
     if (warp < kProducerWarps) {
         // lane = (row within a group of 4, 16-byte chunk of a 128-byte line): one line per quarter warp
         const int rq = lane >> 3, c16 = lane & 7;
-        const float* rowp[4] = {nullptr, nullptr, nullptr, nullptr};   // gathered rows of the current tap (+ chunk offset)
-        int row_next[4];                                               // indices of the next tap, loaded one tap early
-        float4 pre[kPrefetchF][4];
-        uint32_t off[4];
+        const float* rowp[NB];                                         // gathered rows of the current tap (+ chunk offset)
+        int row_next[NB];                                              // indices of the next tap, loaded one tap early
+        float4 pre[kPrefetchF][NB];
+        uint32_t off[NB];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int ml = warp * 16 + b * 4 + rq;                       // row of the tile
+        for (int b = 0; b < NB; ++b) {
+            const int ml = warp * kRowsPerWarp + b * 4 + rq;             // row of the tile
             off[b] = (c16 >> 1) * kA_LBO + (ml >> 3) * 128 + (ml & 7) * 16 + (c16 & 1) * 8;
+            rowp[b] = nullptr;
         }
-        const long long v_first = m0 + warp * 16 + rq;
+        const long long v_first = m0 + warp * kRowsPerWarp + rq;
         auto fetch_rows = [&](int f) {                                 // issue the index loads of tap f (no use yet)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
+            for (int b = 0; b < NB; ++b) {
                 const long long v = v_first + b * 4;
                 int r = -1;
                 if (v < n_out_rows && f < filter_size) r = nbr != nullptr ? load_idx<I64>(nbr, (long long)f * n_out_rows + v) : (int)v;
                 row_next[b] = r;
             }
         };
-        int tap_i = 0, kt_i = 0, issued = 0;                           // issue-side position: tap, K block inside the tap
-        fetch_rows(0);
+        int tap_i = kb_lo / kb_per_tap, kt_i = kb_lo % kb_per_tap, issued = 0;   // issue-side position: tap, K block inside the tap
+        bool adopt = true;                                             // the first issue adopts its tap's rows even mid-tap
+        fetch_rows(tap_i);
         auto issue = [&](float4* dst) {
-            if (kt_i == 0) {                                           // adopt this tap's rows, start fetching the next tap's
+            if (kt_i == 0 || adopt) {                                  // adopt this tap's rows, start fetching the next tap's
+                adopt = false;
 #pragma unroll
-                for (int b = 0; b < 4; ++b)
+                for (int b = 0; b < NB; ++b)
                     rowp[b] = (row_next[b] >= 0 && row_next[b] < n_in_rows) ? in + (long long)row_next[b] * ld_in + 4 * c16 : nullptr;
                 fetch_rows(tap_i + 1);
             }
             const int c = kt_i * TK;
             const bool live = c + 4 * c16 < c_in;
 #pragma unroll
-            for (int b = 0; b < 4; ++b)
+            for (int b = 0; b < NB; ++b)
                 dst[b] = (rowp[b] != nullptr && live) ? __ldg(reinterpret_cast<const float4*>(rowp[b] + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
             ++issued;
             if (++kt_i == kb_per_tap) { kt_i = 0; ++tap_i; }
@@ -234,7 +245,7 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
                 __syncwarp();
                 const uint32_t a_hi = smem_base + stage * kStageBytes;
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {                          // convert + store one chunk at a time (few live registers)
+                for (int b = 0; b < NB; ++b) {                         // convert + store one chunk at a time (few live registers)
                     uint32_t hi[2], lo[2];
                     split4h(pre[d][b], inv_in, hi, lo);
                     sts64(a_hi + off[b], hi[0], hi[1]);
@@ -279,7 +290,7 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
         }
     } else {
         if (lane == 0) {
-            const uint8_t* src = w_image + (long long)n_tile * n_kb * (2 * kBHalf);
+            const uint8_t* src = w_image + ((long long)n_tile * n_kb_total + kb_lo) * (2 * kBHalf);
             int stage = 0;
             uint32_t phase = 0;
             for (int kb = 0; kb < n_kb; ++kb) {
@@ -321,7 +332,24 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
                     y[j] = apply_act(fmaf(sum[j], s_ab, b), act);
                     if (o < c_out) y_max = fmaxf(y_max, fabsf(y[j]));
                 }
-                if (!out_cm) {
+                if (partial) {                                              // K split: add this CTA's partial tile (bias / act later)
+                    if (!out_cm) {
+                        float* p = out + m * ld_out + o0 + cb;
+                        if (o0 + cb + 15 < c_out && (ld_out & 3) == 0 && ((uintptr_t)out & 15) == 0) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4)
+                                red_add_f32x4(p + j, make_float4(sum[j] * s_ab, sum[j + 1] * s_ab, sum[j + 2] * s_ab, sum[j + 3] * s_ab));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (o0 + cb + j < c_out) atomicAdd(p + j, sum[j] * s_ab);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (o0 + cb + j < c_out) atomicAdd(out + (long long)(o0 + cb + j) * ld_out + m, sum[j] * s_ab);
+                    }
+                } else if (!out_cm) {
                     float* p = out + m * ld_out + o0 + cb;
                     if (o0 + cb + 15 < c_out && (ld_out & 3) == 0 && ((uintptr_t)out & 15) == 0) {
 #pragma unroll
@@ -338,12 +366,40 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
                 }
             }
         }
+        if (out_amax != nullptr && !partial) {                              // fused hpl_absmax of the output (next layer's scale)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) y_max = fmaxf(y_max, __shfl_xor_sync(0xffffffffu, y_max, o));
+            if (lane == 0 && y_max > 0.f) atomicMax(out_amax, __float_as_uint(y_max));
+        }
     }
     fence_before();
     __syncthreads();
     if (warp == kProducerWarps) {
         fence_after();
         tmem_dealloc(tmem_d, tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------ bias / activation after a K split
+// out = act(out + bias) in place over (n_rows, channels) vertex-major (ld) or (channels, n_rows) channel-major; max|out|
+// of the result -> amax (may be NULL).
+__global__ void bias_act_kernel(float* __restrict__ out, long long ld, long long n_rows, int channels,
+                                const float* __restrict__ bias, int act, int out_cm, uint32_t* __restrict__ amax) {
+    float m = 0.f;
+    const long long total = (long long)n_rows * channels;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        long long idx;
+        int o;
+        if (out_cm) { o = (int)(t / n_rows); idx = (long long)o * ld + (t - (long long)o * n_rows); }
+        else { const long long v = t / channels; o = (int)(t - v * channels); idx = v * ld + o; }
+        const float y = apply_act(out[idx] + (bias != nullptr ? __ldg(bias + o) : 0.f), act);
+        out[idx] = y;
+        m = fmaxf(m, fabsf(y));
+    }
+    if (amax != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax, __float_as_uint(m));
     }
 }
 
@@ -567,10 +623,12 @@ wgrad_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_r
 void set_attrs() {
     static bool done = false;
     if (done) return;
-    cudaFuncSetAttribute(gather_gemm_f16_kernel<true, 64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    cudaFuncSetAttribute(gather_gemm_f16_kernel<false, 64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    cudaFuncSetAttribute(gather_gemm_f16_kernel<true, 128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (2 * kAHalf + 2 * 128 * TK * 2) + 1024);
-    cudaFuncSetAttribute(gather_gemm_f16_kernel<false, 128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (2 * kAHalf + 2 * 128 * TK * 2) + 1024);
+    cudaFuncSetAttribute(gather_gemm_f16_kernel<true, 64, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaFuncSetAttribute(gather_gemm_f16_kernel<false, 64, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaFuncSetAttribute(gather_gemm_f16_kernel<true, 128, 3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (2 * kAHalf + 2 * 128 * TK * 2) + 1024);
+    cudaFuncSetAttribute(gather_gemm_f16_kernel<false, 128, 3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (2 * kAHalf + 2 * 128 * TK * 2) + 1024);
+    cudaFuncSetAttribute(gather_gemm_f16_kernel<true, 256, 4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (2 * kAHalf + 2 * 256 * TK * 2) + 1024);
+    cudaFuncSetAttribute(gather_gemm_f16_kernel<false, 256, 4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (2 * kAHalf + 2 * 256 * TK * 2) + 1024);
     cudaFuncSetAttribute(wgrad_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmemBytes);
     cudaFuncSetAttribute(wgrad_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmemBytes);
     done = true;
@@ -598,7 +656,7 @@ int hpl_absmax(const float* x, int64_t count, uint32_t* out_bits, void* stream) 
 }
 
 int64_t hpl_blur_gemm_f16_workspace(int64_t filter_size, int64_t c_in, int64_t c_out) {
-    const int64_t kb_per_tap = (c_in + TK - 1) / TK, n_cols = (c_out + 127) / 128 * 128;       // covers both tile widths
+    const int64_t kb_per_tap = (c_in + TK - 1) / TK, n_cols = (c_out + 255) / 256 * 256;       // covers all tile widths
     return n_cols * filter_size * kb_per_tap * 2 * (TK * 2) + 16;      // image + the weight absmax slot
 }
 
@@ -623,28 +681,74 @@ int hpl_blur_gemm_f16_amax(const float* in, int64_t ld_in, int64_t n_in_rows, co
     cudaStream_t s = as_stream(stream);
     set_attrs();
     const int kb_per_tap = (int)((c_in + TK - 1) / TK);
-    const bool wide = c_out >= 128;                          // N = 128 tiles: the gathered operand is staged half as often
-    const int tn = wide ? 128 : 64;
+    // tile width: 64 for narrow layers; 128 for Co >= 128 (the gathered operand is staged half as often); 256 for
+    // Co >= 256 with enough vertices to fill the GPU at one CTA per SM (staged a quarter as often; 16 producer warps)
+    static int wide_knob = -1;                               // HPL_GEMM_TN256=0 disables the 256-wide tile
+    if (wide_knob < 0) { const char* e = getenv("HPL_GEMM_TN256"); wide_knob = e ? atoi(e) : 1; }
+    const long long n_kb_total = filter_size * kb_per_tap;
+    const bool tn256 = wide_knob != 0 && c_out >= 256 && n_out_rows >= 64LL * TM;
+    const bool wide = c_out >= 128;
+    const int tn = tn256 ? 256 : (wide ? 128 : 64);
     const long long n_tiles = (c_out + tn - 1) / tn;
-    const long long image_bytes = n_tiles * filter_size * kb_per_tap * 2 * (tn * TK * 2);
+    const long long image_bytes = n_tiles * n_kb_total * 2 * (tn * TK * 2);
     uint8_t* image = reinterpret_cast<uint8_t*>(workspace);
     uint32_t* w_amax = reinterpret_cast<uint32_t*>(image + image_bytes);
     const long long w_count = filter_size * c_in * c_out;
     const int rc = hpl_absmax(w, w_count, w_amax, stream);
     if (rc != 0) return rc;
-    const long long chunks = n_tiles * filter_size * kb_per_tap * (tn * (TK / 8));
-    if (wide)
-        weight_image16_kernel<128><<<(unsigned)((chunks + 255) / 256), 256, 0, s>>>(w, w_sf, w_sc, w_so, (int)filter_size, (int)c_in, (int)c_out, kb_per_tap, w_amax, image);
+    const long long chunks = n_tiles * n_kb_total * (tn * (TK / 8));
+    const unsigned img_blocks = (unsigned)((chunks + 255) / 256);
+    if (tn256)
+        weight_image16_kernel<256><<<img_blocks, 256, 0, s>>>(w, w_sf, w_sc, w_so, (int)filter_size, (int)c_in, (int)c_out, kb_per_tap, w_amax, image);
+    else if (wide)
+        weight_image16_kernel<128><<<img_blocks, 256, 0, s>>>(w, w_sf, w_sc, w_so, (int)filter_size, (int)c_in, (int)c_out, kb_per_tap, w_amax, image);
     else
-        weight_image16_kernel<64><<<(unsigned)((chunks + 255) / 256), 256, 0, s>>>(w, w_sf, w_sc, w_so, (int)filter_size, (int)c_in, (int)c_out, kb_per_tap, w_amax, image);
-    const long long steps = (long long)filter_size * kb_per_tap * (TK / 16);
+        weight_image16_kernel<64><<<img_blocks, 256, 0, s>>>(w, w_sf, w_sc, w_so, (int)filter_size, (int)c_in, (int)c_out, kb_per_tap, w_amax, image);
+    const long long steps = n_kb_total * (TK / 16);
+    const long long m_tiles = (n_out_rows + TM - 1) / TM;
+    if (tn256) {
+        // TMEM (512 columns) holds ONE main accumulator at this width, good for <= ~180 accumulate steps: longer K ranges
+        // are split over blockIdx.z, partial tiles are summed in `out` by fp32 RED, bias / activation / statistics follow
+        // in bias_act_kernel.
+        const int max_kb = 180 / (TK / 16);
+        const long long splits = (n_kb_total + max_kb - 1) / max_kb;
+        const int kb_per_split = splits > 1 ? (int)((n_kb_total + splits - 1) / splits) : 0;
+        const long long z = splits > 1 ? (n_kb_total + kb_per_split - 1) / kb_per_split : 1;
+        HPL_CHECK_ARG(z <= 65535);
+        dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)z);
+        constexpr int kSt = 4, kPW = 16;
+        const int smem = kSt * (2 * kAHalf + 2 * 256 * TK * 2) + 1024;
+        if (z > 1) {
+            const long long bytes = 4LL * (out_channel_major ? c_out * ld_out : n_out_rows * ld_out);
+            cudaError_t e = cudaMemsetAsync(out, 0, (size_t)bytes, s);
+            if (e != cudaSuccess) return (int)e;
+        }
+        const float* k_bias = z > 1 ? nullptr : bias;
+        const int k_act = z > 1 ? HPL_ACT_NONE : act;
+        uint32_t* k_amax = z > 1 ? nullptr : out_amax;
+        if (idx64)
+            gather_gemm_f16_kernel<true, 256, kSt, kPW><<<grid, kPW * 32 + 64, smem, s>>>(
+                in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, (int)c_in, (int)c_out, kb_per_tap, image, k_bias, k_act, out,
+                ld_out, out_channel_major, 1, in_amax, w_amax, k_amax, kb_per_split);
+        else
+            gather_gemm_f16_kernel<false, 256, kSt, kPW><<<grid, kPW * 32 + 64, smem, s>>>(
+                in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, (int)c_in, (int)c_out, kb_per_tap, image, k_bias, k_act, out,
+                ld_out, out_channel_major, 1, in_amax, w_amax, k_amax, kb_per_split);
+        if (z > 1 && (bias != nullptr || act != HPL_ACT_NONE || out_amax != nullptr)) {
+            const long long total = out_channel_major ? c_out * n_out_rows : n_out_rows * c_out;
+            long long blocks = (total + 255) / 256;
+            if (blocks > 16LL * num_sms()) blocks = 16LL * num_sms();
+            bias_act_kernel<<<(unsigned)blocks, 256, 0, s>>>(out, ld_out, n_out_rows, (int)c_out, bias, act, out_channel_major, out_amax);
+        }
+        HPL_RETURN_LAST();
+    }
     // accumulate steps per hi.hi accumulator <= ~160-190; TMEM holds (n_main + 1) * tn <= 512 columns
     const int n_main = steps <= 160 ? 1 : ((steps <= 480 || wide) ? 3 : 7);
-    dim3 grid((unsigned)((n_out_rows + TM - 1) / TM), (unsigned)n_tiles);
+    dim3 grid((unsigned)m_tiles, (unsigned)n_tiles);
 #define HPL_LAUNCH_F16(I64, TNV, ST)                                                                                         \
-    gather_gemm_f16_kernel<I64, TNV, ST><<<grid, kThreads, ST * (2 * kAHalf + 2 * TNV * TK * 2) + 1024, s>>>(                \
+    gather_gemm_f16_kernel<I64, TNV, ST, 8><<<grid, kThreads, ST * (2 * kAHalf + 2 * TNV * TK * 2) + 1024, s>>>(             \
         in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, (int)c_in, (int)c_out, kb_per_tap, image, bias, act, out,   \
-        ld_out, out_channel_major, n_main, in_amax, w_amax, out_amax)
+        ld_out, out_channel_major, n_main, in_amax, w_amax, out_amax, 0)
     if (wide) {
         if (idx64) HPL_LAUNCH_F16(true, 128, 3); else HPL_LAUNCH_F16(false, 128, 3);
     } else {

@@ -111,3 +111,64 @@ def test_h16_split_reconstructs_fp32(h, c):
     rec = (planes[:, 0] + planes[:, 1] * 2.0 ** -11) * s
     assert (rec[:h, :c] - x[:, :c]).abs().max().item() <= m * 2.0 ** -21
     assert rec[h].abs().max().item() == 0 and (c == ld16 or rec[:, c:].abs().max().item() == 0)
+
+
+@pytest.mark.parametrize("h,c,co,f,act,cm", [
+    (9000, 64, 256, 15, ops.ACT_LEAKY, False),     # 256-wide tile, one K range (30 K blocks)
+    (8200, 580, 300, 15, ops.ACT_LEAKY, False),    # K = 8700 split over 4 CTAs per tile (RED partial sums), ragged Co
+    (8300, 324, 512, 15, ops.ACT_NONE, True),      # split K, channel-major output (bcn2_-like)
+    (8192, 1024, 512, 1, ops.ACT_RELU, False),     # 1x1 layer (conv3-like)
+])
+def test_wide_tile_engine2_matches_float64(h, c, co, f, act, cm):
+    """Engine 2's 256-wide tile (Co >= 256, >= 8192 rows): 16 producer warps, one CTA per SM, K split over blockIdx.z
+    with bias / activation / max|out| applied by the follow-up pass."""
+    torch.manual_seed(h + co)
+    x = ops.alloc_rows(h, c, DEV, zero=True)
+    x[:, :c] = torch.randn(h, c, device=DEV)
+    w = torch.randn(f, c, co, device=DEV) * (f * c) ** -0.5
+    bias = torch.randn(co, device=DEV)
+    nbr = None
+    if f > 1:
+        nbr = torch.randint(-1, h, (f, h), device=DEV, dtype=torch.int32)
+        nbr[0] = torch.arange(h, device=DEV)
+    slot = ops.amax_slots(DEV, 1)
+    y = ops.blur_gemm(x, c, nbr, h, w, bias, act, out_channel_major=cm, precision=2, out_amax=slot)
+    got = y.t()[:, :co] if cm else y[:, :co]
+    want = _reference(x, nbr, w, bias, act)
+    assert_close(got, want, "wide tile")
+    assert slot.view(torch.float32).item() == got.abs().max().item()           # the fused statistic is exact
+    # strided weight operand: the same result from a permuted view of the conv-layout weight
+    w_conv = w.permute(2, 1, 0).contiguous()                                    # (Co, C, F) like nn.Conv2d's weight
+    y2 = ops.blur_gemm(x, c, nbr, h, w_conv.permute(2, 1, 0), bias, act, out_channel_major=cm, precision=2)
+    assert_close(y2.t()[:, :co] if cm else y2[:, :co], want, "strided weight")
+
+
+@pytest.mark.parametrize("h,c,co,f", [(7599, 64, 64, 15), (4097, 128, 200, 1), (333, 20, 32, 15)])
+def test_epilogue_amax_is_exact(h, c, co, f):
+    """The GEMM epilogue's fused statistic equals max|out| (it scales the next layer's FP16 split)."""
+    torch.manual_seed(h)
+    x = ops.alloc_rows(h, c, DEV, zero=True)
+    x[:, :c] = torch.randn(h, c, device=DEV) * 300.0
+    w = torch.randn(f, c, co, device=DEV)
+    nbr = torch.randint(-1, h, (f, h), device=DEV, dtype=torch.int32) if f > 1 else None
+    slot = ops.amax_slots(DEV, 1)
+    y = ops.blur_gemm(x, c, nbr, h, w, None, ops.ACT_LEAKY, precision=2, out_amax=slot)
+    assert slot.view(torch.float32).item() == y[:, :co].abs().max().item() > 1000.0
+
+
+def test_stack_scales_follow_large_activations():
+    """Two chained layers whose intermediate activations are ~1e5 (beyond fp16 range unless the second layer's operand
+    scale comes from the first layer's fused statistic)."""
+    from hplflownet_b200 import _stack
+    h, c = 5000, 64
+    torch.manual_seed(3)
+    x = ops.alloc_rows(h, c, DEV, zero=True)
+    x[:, :c] = torch.randn(h, c, device=DEV) * 1.0e4
+    nbr = torch.randint(-1, h, (15, h), device=DEV, dtype=torch.int32)
+    w1, w2 = torch.randn(15, c, 64, device=DEV), torch.randn(1, 64, 32, device=DEV) * 0.1
+    b1, b2 = torch.randn(64, device=DEV), torch.randn(32, device=DEV)
+    xs, chans, _ = _stack.forward(x, c, h, [(w1, b1, ops.ACT_LEAKY), (w2, b2, ops.ACT_NONE)], nbr)
+    mid = _reference(x, nbr, w1, b1, ops.ACT_LEAKY)
+    assert mid.abs().max().item() > 65504.0
+    want = mid @ w2[0].double() + b2.double()
+    assert_close(xs[-1][:, :32], want, "chained layers")

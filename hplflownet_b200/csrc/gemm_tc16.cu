@@ -406,22 +406,30 @@ __global__ void bias_act_kernel(float* __restrict__ out, long long ld, long long
 // ------------------------------------------------------------------------------ weight gradient
 // dw[(f,c), o] += sum_v in[nbr[f,v], c] * dz[v, o];  both operands MN-major no-swizzle fp16:
 //   element (m, k) at (k / 8) * LBO + (m / 8) * 128 + (k % 8) * 16 + (m % 8) * 2
-constexpr int WG_MAIN = 3;
 constexpr int kWStages = 3;
 constexpr uint32_t kW_SBO = 128 + 32;                       // MN-chunk stride, padded (bank spreading)
 constexpr uint32_t kWA_LBO = (TM / 8) * kW_SBO;             // 2560: next 8 vertices of the A tile
-constexpr uint32_t kWB_LBO = (TN / 8) * kW_SBO;             // 1280
 constexpr int kWAHalf = (TK / 8) * kWA_LBO;                 // 10240
-constexpr int kWBHalf = (TK / 8) * kWB_LBO;                 // 5120
-constexpr int kWStageBytes = 2 * kWAHalf + 2 * kWBHalf;     // 30720
-constexpr int kWSmemBytes = kWStages * kWStageBytes + 1024;
+template <int TNv> struct WCfg {
+    static constexpr uint32_t kB_LBO = (TNv / 8) * kW_SBO;  // 1280 (N = 64) / 5120 (N = 256)
+    static constexpr int kBHalf = (TK / 8) * kB_LBO;        // 5120 / 20480
+    static constexpr int kStageBytes = 2 * kWAHalf + 2 * kBHalf;
+    static constexpr int kSmemBytes = kWStages * kStageBytes + 1024;
+};
 
-template <bool I64>
-__global__ void __launch_bounds__(kThreads, 2)
+// TNv = 64, PW = 8 producer warps, MAINS = 3 (two CTAs per SM) -- or the wide tile for Co >= 256: TNv = 256, PW = 16,
+// MAINS = 1 (one CTA per SM; the gathered operand is staged a quarter as often, vertex ranges of <= 2560 per CTA).
+template <bool I64, int TNv, int PW, int MAINS>
+__global__ void __launch_bounds__(PW * 32 + 64, PW == 8 ? 2 : 1)
 wgrad_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_rows, const void* __restrict__ nbr,
                  int filter_size, long long n_out_rows, int c_in, int c_out, const float* __restrict__ dz, long long ld_dz,
                  float* __restrict__ dw, long long rows_per_split, const uint32_t* __restrict__ in_amax,
                  const uint32_t* __restrict__ dz_amax) {
+    constexpr int TN = TNv, kProducerWarps = PW, WG_MAIN = MAINS;
+    using W = WCfg<TNv>;
+    constexpr uint32_t kWB_LBO = W::kB_LBO;
+    constexpr int kWBHalf = W::kBHalf, kWStageBytes = W::kStageBytes;
+    constexpr uint32_t kIdescMN = instr_desc(0, TM, TN, 1, 1);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t full_bar[kWStages], empty_bar[kWStages], accum_bar;
@@ -458,28 +466,32 @@ wgrad_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_r
     scale_from_amax(__ldg(dz_amax), s_dz, inv_dz);
 
     if (warp < kProducerWarps) {
-        // lane = (vertex within a group of 4, 16-byte chunk of a 128-byte line): one line per quarter warp
+        // lane = (vertex within a group of 4, 16-byte chunk of a 128-byte line): one line per quarter warp.
+        // Warp w owns vertex quad w % 8 of the stage (vertices 4q..4q+3) and six line tasks per vertex:
+        //   warps 0-7 : the 4 segments of 32 M rows of the gathered operand + output segments 0, 1 of dz
+        //   warps 8-15: output segments 2..7 of dz (N = 256 only)
         const int rq = lane >> 3, c16 = lane & 7;
-        // Warp w owns vertex quad w of the stage (vertices 4w..4w+3); its 4 A tasks are the 4 segments of 32 M rows,
-        // its 2 B tasks the 2 segments of 32 outputs -> one vertex offset and one smem base per operand.
-        const int kk = warp * 4 + rq;                                  // vertex inside the stage
-        const uint32_t sm_row = (warp >> 1) * 1u, sm_in = ((warp & 1) * 4 + rq) * 16 + (c16 & 1) * 8;
+        const int wq = warp & 7;
+        const bool a_group = warp < 8;
+        const int bseg0 = a_group ? 0 : 2;                             // first dz segment of this warp
+        const int kk = wq * 4 + rq;                                    // vertex inside the stage
+        const uint32_t sm_row = (wq >> 1) * 1u, sm_in = ((wq & 1) * 4 + rq) * 16 + (c16 & 1) * 8;
         const uint32_t base_a = sm_row * kWA_LBO + (c16 >> 1) * kW_SBO + sm_in;     // + seg * 4 * kW_SBO
-        const uint32_t base_b = sm_row * kWB_LBO + (c16 >> 1) * kW_SBO + sm_in;
+        const uint32_t base_b = sm_row * kWB_LBO + (c16 >> 1) * kW_SBO + sm_in + bseg0 * 4 * kW_SBO;
         int ch[4];                                                     // channel of this lane's chunk per segment, -1 = beyond M
         unsigned ipos[4];                                              // element offset into nbr + v_lo (32-bit; host checks the range)
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const int m = m0 + t * 32 + 4 * c16;
-            const int tp = m < m_total ? m / c_in : -1;
+            const int tp = (a_group && m < m_total) ? m / c_in : -1;
             ch[t] = tp >= 0 ? m - tp * c_in : -1;
             ipos[t] = (unsigned)((nbr != nullptr && tp >= 0 ? (long long)tp * n_out_rows : 0) + kk);
         }
-        unsigned zpos = (unsigned)(kk * ld_dz + o0 + 4 * c16);          // element offset into dz + v_lo * ld_dz; segment t adds 32
-        const bool b_ok0 = o0 + 4 * c16 < c_out, b_ok1 = o0 + 32 + 4 * c16 < c_out;
+        unsigned zpos = (unsigned)(kk * ld_dz + o0 + 32 * bseg0 + 4 * c16);   // element offset into dz + v_lo * ld_dz; segment t adds 32
+        const int o_first = o0 + 32 * bseg0 + 4 * c16;
         const float* dz_base = dz + v_lo * ld_dz;
 
-        float4 pre[kPrefetch][6];
+        float4 pre[kPrefetch][6];                                      // a_group: 4 gathered + 2 dz lines; else 6 dz lines
         int idx_next[4];                                               // gathered-row indices of the next stage to issue
         const int span = (int)(v_hi - v_lo);                           // vertices of this CTA
         int fetched = 0, issued = 0;                                   // stages whose indices / data have been requested
@@ -495,20 +507,29 @@ wgrad_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_r
             }
             ++fetched;
         };
-        fetch_idx();
+        if (a_group) fetch_idx();
         auto issue = [&](float4* dst) {
             const int base = issued * TK;
-            int rr[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) rr[t] = idx_next[t] < n_in_rows ? idx_next[t] : -1;
-            fetch_idx();
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-                dst[t] = rr[t] >= 0 ? __ldg(reinterpret_cast<const float4*>(in + (long long)rr[t] * ld_in + ch[t]))
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
             const bool v_ok = base + kk < span;
-            dst[4] = (v_ok && b_ok0) ? __ldg(reinterpret_cast<const float4*>(dz_base + zpos)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            dst[5] = (v_ok && b_ok1) ? __ldg(reinterpret_cast<const float4*>(dz_base + zpos + 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a_group) {
+                int rr[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) rr[t] = idx_next[t] < n_in_rows ? idx_next[t] : -1;
+                fetch_idx();
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    dst[t] = rr[t] >= 0 ? __ldg(reinterpret_cast<const float4*>(in + (long long)rr[t] * ld_in + ch[t]))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int t = 0; t < 2; ++t)
+                    dst[4 + t] = (v_ok && o_first + 32 * t < c_out) ? __ldg(reinterpret_cast<const float4*>(dz_base + zpos + 32 * t))
+                                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+#pragma unroll
+                for (int t = 0; t < 6; ++t)
+                    dst[t] = (v_ok && o_first + 32 * t < c_out) ? __ldg(reinterpret_cast<const float4*>(dz_base + zpos + 32 * t))
+                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             zpos += (unsigned)(TK * ld_dz);
             ++issued;
         };
@@ -525,21 +546,32 @@ wgrad_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_r
                 if (lane0) mbar_wait_a(empty_a + 8 * stage, phase ^ 1);
                 __syncwarp();
                 const uint32_t a_hi = smem_base + stage * kWStageBytes;
+                const uint32_t b_hi = a_hi + 2 * kWAHalf;
                 // convert and store one chunk at a time (keeps the live registers low: this kernel holds
                 // 12 gathered float4 per thread), then refill the slot with the loads of a later stage
+                if (a_group) {
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    uint32_t hi[2], lo[2];
-                    split4h(pre[d][t], inv_in, hi, lo);
-                    sts64(a_hi + base_a + t * 4 * kW_SBO, hi[0], hi[1]);
-                    sts64(a_hi + kWAHalf + base_a + t * 4 * kW_SBO, lo[0], lo[1]);
-                }
+                    for (int t = 0; t < 4; ++t) {
+                        uint32_t hi[2], lo[2];
+                        split4h(pre[d][t], inv_in, hi, lo);
+                        sts64(a_hi + base_a + t * 4 * kW_SBO, hi[0], hi[1]);
+                        sts64(a_hi + kWAHalf + base_a + t * 4 * kW_SBO, lo[0], lo[1]);
+                    }
 #pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    uint32_t hi[2], lo[2];
-                    split4h(pre[d][4 + t], inv_dz, hi, lo);
-                    sts64(a_hi + 2 * kWAHalf + base_b + t * 4 * kW_SBO, hi[0], hi[1]);
-                    sts64(a_hi + 2 * kWAHalf + kWBHalf + base_b + t * 4 * kW_SBO, lo[0], lo[1]);
+                    for (int t = 0; t < 2; ++t) {
+                        uint32_t hi[2], lo[2];
+                        split4h(pre[d][4 + t], inv_dz, hi, lo);
+                        sts64(b_hi + base_b + t * 4 * kW_SBO, hi[0], hi[1]);
+                        sts64(b_hi + kWBHalf + base_b + t * 4 * kW_SBO, lo[0], lo[1]);
+                    }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 6; ++t) {
+                        uint32_t hi[2], lo[2];
+                        split4h(pre[d][t], inv_dz, hi, lo);
+                        sts64(b_hi + base_b + t * 4 * kW_SBO, hi[0], hi[1]);
+                        sts64(b_hi + kWBHalf + base_b + t * 4 * kW_SBO, lo[0], lo[1]);
+                    }
                 }
                 if (issued < n_kb) issue(pre[d]);
                 fence_proxy_async();
@@ -586,6 +618,7 @@ wgrad_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_r
         const float s_ab = s_in * s_dz;
 #pragma unroll 1
         for (int cb = 0; cb < TN; cb += 16) {
+            if (o0 + cb >= c_out) break;
             float sum[16];
             uint32_t v[16];
             tmem_ld16(taddr + cb, v);
@@ -629,8 +662,10 @@ void set_attrs() {
     cudaFuncSetAttribute(gather_gemm_f16_kernel<false, 128, 3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (2 * kAHalf + 2 * 128 * TK * 2) + 1024);
     cudaFuncSetAttribute(gather_gemm_f16_kernel<true, 256, 4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (2 * kAHalf + 2 * 256 * TK * 2) + 1024);
     cudaFuncSetAttribute(gather_gemm_f16_kernel<false, 256, 4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (2 * kAHalf + 2 * 256 * TK * 2) + 1024);
-    cudaFuncSetAttribute(wgrad_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmemBytes);
-    cudaFuncSetAttribute(wgrad_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmemBytes);
+    cudaFuncSetAttribute(wgrad_f16_kernel<true, 64, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, WCfg<64>::kSmemBytes);
+    cudaFuncSetAttribute(wgrad_f16_kernel<false, 64, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, WCfg<64>::kSmemBytes);
+    cudaFuncSetAttribute(wgrad_f16_kernel<true, 256, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WCfg<256>::kSmemBytes);
+    cudaFuncSetAttribute(wgrad_f16_kernel<false, 256, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WCfg<256>::kSmemBytes);
     done = true;
 }
 
@@ -767,27 +802,34 @@ int hpl_blur_wgrad_f16(const float* in, int64_t ld_in, int64_t n_in_rows, const 
     HPL_CHECK_ARG(nbr != nullptr || filter_size == 1);
     if (n_out_rows == 0) return 0;
     set_attrs();
-    const long long m_tiles = (filter_size * c_in + TM - 1) / TM, n_tiles = (c_out + TN - 1) / TN;
+    static int wide_knob = -1;                               // HPL_GEMM_TN256=0 disables the 256-wide tile
+    if (wide_knob < 0) { const char* e = getenv("HPL_GEMM_TN256"); wide_knob = e ? atoi(e) : 1; }
+    const bool tn256 = wide_knob != 0 && c_out >= 256 && n_out_rows >= 64LL * TM;
+    const int tn = tn256 ? 256 : TN, n_mains = tn256 ? 1 : 3;
+    const long long m_tiles = (filter_size * c_in + TM - 1) / TM, n_tiles = (c_out + tn - 1) / tn;
     const long long base = m_tiles * n_tiles;
-    long long splits = (4LL * num_sms() + base - 1) / base;
+    long long splits = ((tn256 ? 2LL : 4LL) * num_sms() + base - 1) / base;
     const long long max_splits = (n_out_rows + 8 * TK - 1) / (8 * TK);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     long long rows_per_split = (n_out_rows + splits - 1) / splits;
     rows_per_split = (rows_per_split + TK - 1) / TK * TK;
-    const long long max_rows = 160LL * WG_MAIN * 16;                       // <= ~160 accumulate steps (K = 16) per accumulator
+    const long long max_rows = 160LL * n_mains * 16;                       // <= ~160 accumulate steps (K = 16) per accumulator
     if (rows_per_split > max_rows) rows_per_split = max_rows;
     splits = (n_out_rows + rows_per_split - 1) / rows_per_split;
     HPL_CHECK_ARG(splits <= 65535 && n_tiles <= 65535);
     HPL_CHECK_ARG(filter_size * n_out_rows < (1LL << 31) && (rows_per_split + TK) * ld_dz < (1LL << 31));   // 32-bit in-kernel offsets
     dim3 grid((unsigned)m_tiles, (unsigned)splits, (unsigned)n_tiles);
     cudaStream_t s = as_stream(stream);
-    if (idx64)
-        wgrad_f16_kernel<true><<<grid, kThreads, kWSmemBytes, s>>>(in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, (int)c_in, (int)c_out, dz,
-                                                                  ld_dz, dw, rows_per_split, in_amax, dz_amax);
-    else
-        wgrad_f16_kernel<false><<<grid, kThreads, kWSmemBytes, s>>>(in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, (int)c_in, (int)c_out, dz,
-                                                                   ld_dz, dw, rows_per_split, in_amax, dz_amax);
+#define HPL_LAUNCH_WG(I64, TNV, PWV, MN)                                                                                          \
+    wgrad_f16_kernel<I64, TNV, PWV, MN><<<grid, PWV * 32 + 64, WCfg<TNV>::kSmemBytes, s>>>(                                       \
+        in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, (int)c_in, (int)c_out, dz, ld_dz, dw, rows_per_split, in_amax, dz_amax)
+    if (tn256) {
+        if (idx64) HPL_LAUNCH_WG(true, 256, 16, 1); else HPL_LAUNCH_WG(false, 256, 16, 1);
+    } else {
+        if (idx64) HPL_LAUNCH_WG(true, 64, 8, 3); else HPL_LAUNCH_WG(false, 64, 8, 3);
+    }
+#undef HPL_LAUNCH_WG
     if (db != nullptr) return hpl_column_sums(dz, ld_dz, n_out_rows, c_out, db, stream);
     HPL_RETURN_LAST();
 }

@@ -172,3 +172,24 @@ def test_stack_scales_follow_large_activations():
     assert mid.abs().max().item() > 65504.0
     want = mid @ w2[0].double() + b2.double()
     assert_close(xs[-1][:, :32], want, "chained layers")
+
+
+@pytest.mark.parametrize("h,c,co,f", [
+    (8200, 64, 256, 15),        # 256-wide weight-gradient tile: 16 producer warps, one main accumulator
+    (8300, 324, 512, 15),       # M tiles straddle taps, two N tiles
+    (8192, 1024, 300, 1),       # 1x1 layer, ragged Co (second N tile 44 wide)
+    (20000, 68, 260, 15),       # several vertex ranges per tile column, ragged everything
+])
+def test_wide_tile_wgrad_matches_float64(h, c, co, f):
+    torch.manual_seed(h + co)
+    x = ops.alloc_rows(h, c, DEV, zero=True)
+    x[:, :c] = torch.randn(h, c, device=DEV)
+    dz = ops.alloc_rows(h, co, DEV, zero=True)
+    dz[:, :co] = torch.randn(h, co, device=DEV)
+    nbr = torch.randint(-1, h, (f, h), device=DEV, dtype=torch.int32) if f > 1 else None
+    dw, db = ops.blur_wgrad(x, c, nbr, h, dz, co, f, precision=2)
+    xd = torch.cat((x.double(), torch.zeros(1, x.size(1), dtype=torch.float64, device=DEV)), 0)
+    g = xd[:h, :c][None] if nbr is None else xd[nbr.long()][:, :, :c]
+    want = torch.einsum("fvc,vo->fco", g, dz[:, :co].double())
+    assert_close(dw, want, "wide wgrad")
+    assert_close(db, dz[:, :co].double().sum(0), "bias grad")

@@ -23,6 +23,18 @@
 // Each lane then owns 4 consecutive K (or M) elements = half of a 16-byte operand chunk and stores hi / lo
 // with 8-byte STS; the chunk strides (LBO / SBO, free parameters of the UMMA descriptor) are padded by 32
 // bytes so that the 4 chunks a half warp touches fall into 4 different bank groups (conflict-free).
+//
+// Tile widths.  N = 64 (narrow layers, two CTAs of 8 producer warps per SM), N = 128 (Co >= 128), and N = 256 for
+// Co >= 256 with >= 8192 rows: ONE CTA of 16 producer warps per SM, so the gathered operand is loaded and split a
+// quarter as often per output.  At N = 256 tensor memory (512 columns) holds the cross accumulator plus a single main
+// accumulator, which is exact for <= ~180 accumulate steps: the forward kernel splits longer K ranges over
+// blockIdx.z (partial tiles summed in the zeroed output by fp32 RED, bias / activation / statistics by
+// bias_act_kernel), the weight gradient limits its vertex range per CTA to 2560.
+//
+// Statistics.  The scale of every operand tensor comes from max|x|; the forward epilogue records max|out| for the
+// next layer (RED.MAX per warp), see also rows.cu (act_backward_stats_kernel) -- no separate absmax passes between
+// layers.  The weight operand is read strided (any dense permutation of (F, C, Co)), so the reference's conv-layout
+// weights and their transposes for the data gradient are consumed in place.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 

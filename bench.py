@@ -239,6 +239,10 @@ def run_ours(args):
 
     # ---- value: inputs resident (the clock sampler starts before warm-up: nvidia-smi needs ~100 ms to
     # deliver its first sample, and warm-up is the same load)
+    # The headline loops rebuild the weight images on every call (the per-parameter image cache of ops.py would skip
+    # two small kernels per GEMM because the weights never change here); the model / training legs below use the cache
+    # the way a deployment does (evaluation: constant weights; training: one rebuild per optimisation step).
+    ops.WEIGHT_CACHE = False
     sampler = ClockSampler(local)
     if rank == 0 and os.environ.get("HPL_BENCH_NO_SMI") != "1":
         sampler.start()
@@ -302,6 +306,7 @@ def run_ours(args):
     d2h = 4 + sum(p.numel() * 4 for p in params)
 
     # ---- secondary, all ranks: data-parallel HPLFlowNet training step (BASELINE configs[4])
+    ops.WEIGHT_CACHE = True
     train = train_leg(dev, rank, world)
 
     # ---- max over ranks
@@ -362,7 +367,8 @@ def run_ours(args):
                    "clouds_per_gpu_per_step": B, "points_per_step_per_gpu": n_tot, "vertices_per_step_per_gpu": h_tot,
                    "l2_policy": "inputs larger than L2 (working set %.0f MB per step)" % (
                        4e-6 * (2 * n_tot * CHANNELS + 2 * h_tot * CHANNELS)),
-                   "index_dtype": "int64 (reference format)"},
+                   "index_dtype": "int64 (reference format)",
+                   "weight_images": "rebuilt on every call in the timed loops (cache disabled)"},
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "clouds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps},

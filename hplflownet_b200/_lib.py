@@ -32,7 +32,7 @@ SIGNATURES = {
     "hpl_split16": [vp, i64, i64, i64, vp, vp, vp],
     "hpl_blur_gemm_p16": [vp, i64, vp, cint, i64, i64, i64, i64, vp, vp, cint, vp, i64, cint, vp, vp, vp],
     "hpl_blur_wgrad_p16": [vp, i64, vp, cint, i64, i64, i64, i64, vp, vp, vp, vp, vp],
-    "hpl_blur_gemm_f16_amax": [vp, i64, i64, vp, cint, i64, i64, i64, i64, vp, i64, i64, i64, vp, cint, vp, i64, cint, vp, vp, vp, vp],
+    "hpl_blur_gemm_f16_amax": [vp, i64, i64, vp, cint, i64, i64, i64, i64, vp, i64, i64, i64, vp, cint, vp, i64, cint, vp, cint, vp, vp, vp],
     "hpl_normalize_rows_amax": [vp, i64, i64, i64, vp, vp, vp, vp],
     "hpl_cm_to_rows_amax": [vp, i64, i64, i64, vp, i64, vp, vp],
     "hpl_act_backward_stats": [vp, i64, vp, i64, i64, i64, cint, vp, vp, vp],

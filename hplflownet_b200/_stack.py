@@ -80,6 +80,9 @@ def backward(dx, xs, chans, layers, n_rows, first_nbr, first_nbr_t, need_input_g
                 grads[l] = (grads[l][0], db_fused)
         if l > 0 or need_input_grad:
             wd = w.transpose(1, 2)                                    # (F, Co, C) view
+            owner = getattr(w, "_hpl_owner", None)
+            if owner is not None:
+                ops.with_owner(wd, owner[0], "dgrad")
             tbl_t = first_nbr_t() if (l == 0 and first_nbr is not None) else None
             n_in = xs[l].size(0)
             dx = ops.blur_gemm(dx, chans[l + 1], tbl_t, n_in, wd, None, ops.ACT_NONE, tag="dgrad", x_amax=dz_amax, x16=dz16)

@@ -70,7 +70,7 @@ def conv2d_layers(module_list, use_leaky):
 def kernel_weight(w):
     """(Co, C, F, 1) conv weight -> its (F, C, Co) VIEW, the operand of the gather-GEMM (engine 2 reads it strided;
     ops.blur_gemm makes a contiguous copy for the engines that need one)."""
-    return w.detach().reshape(w.size(0), w.size(1), -1).permute(2, 1, 0)
+    return ops.with_owner(w.detach().reshape(w.size(0), w.size(1), -1).permute(2, 1, 0), w, "fwd")
 
 
 def conv_weight_grad(dw, like):

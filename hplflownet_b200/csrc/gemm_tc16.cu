@@ -711,13 +711,13 @@ int hpl_blur_gemm_f16(const float* in, int64_t ld_in, int64_t n_in_rows, const v
                       int64_t n_out_rows, int64_t c_in, int64_t c_out, const float* w, const float* bias, int act, float* out,
                       int64_t ld_out, int out_channel_major, void* workspace, const uint32_t* in_amax, void* stream) {
     return hpl_blur_gemm_f16_amax(in, ld_in, n_in_rows, nbr, idx64, filter_size, n_out_rows, c_in, c_out, w, 0, 0, 0, bias, act, out,
-                                  ld_out, out_channel_major, workspace, in_amax, nullptr, stream);
+                                  ld_out, out_channel_major, workspace, 0, in_amax, nullptr, stream);
 }
 
 int hpl_blur_gemm_f16_amax(const float* in, int64_t ld_in, int64_t n_in_rows, const void* nbr, int idx64, int64_t filter_size,
                            int64_t n_out_rows, int64_t c_in, int64_t c_out, const float* w, int64_t w_sf, int64_t w_sc, int64_t w_so,
                            const float* bias, int act, float* out, int64_t ld_out, int out_channel_major, void* workspace,
-                           const uint32_t* in_amax, uint32_t* out_amax, void* stream) {
+                           int workspace_valid, const uint32_t* in_amax, uint32_t* out_amax, void* stream) {
     if (w_sf == 0 && w_sc == 0 && w_so == 0) { w_sf = c_in * c_out; w_sc = c_out; w_so = 1; }   // contiguous (F, C, Co)
     HPL_CHECK_ARG(in && w && out && workspace && in_amax && c_in > 0 && c_out > 0 && filter_size > 0 && c_in % 4 == 0);
     HPL_CHECK_ARG(ld_in % 4 == 0 && ld_in >= c_in && ((uintptr_t)in & 15) == 0 && ((uintptr_t)workspace & 15) == 0);
@@ -740,17 +740,19 @@ int hpl_blur_gemm_f16_amax(const float* in, int64_t ld_in, int64_t n_in_rows, co
     const long long image_bytes = n_tiles * n_kb_total * 2 * (tn * TK * 2);
     uint8_t* image = reinterpret_cast<uint8_t*>(workspace);
     uint32_t* w_amax = reinterpret_cast<uint32_t*>(image + image_bytes);
-    const long long w_count = filter_size * c_in * c_out;
-    const int rc = hpl_absmax(w, w_count, w_amax, stream);
-    if (rc != 0) return rc;
-    const long long chunks = n_tiles * n_kb_total * (tn * (TK / 8));
-    const unsigned img_blocks = (unsigned)((chunks + 255) / 256);
-    if (tn256)
-        weight_image16_kernel<256><<<img_blocks, 256, 0, s>>>(w, w_sf, w_sc, w_so, (int)filter_size, (int)c_in, (int)c_out, kb_per_tap, w_amax, image);
-    else if (wide)
-        weight_image16_kernel<128><<<img_blocks, 256, 0, s>>>(w, w_sf, w_sc, w_so, (int)filter_size, (int)c_in, (int)c_out, kb_per_tap, w_amax, image);
-    else
-        weight_image16_kernel<64><<<img_blocks, 256, 0, s>>>(w, w_sf, w_sc, w_so, (int)filter_size, (int)c_in, (int)c_out, kb_per_tap, w_amax, image);
+    if (!workspace_valid) {                                  // (the caller may keep the image of an unchanged weight: same n_out_rows class)
+        const long long w_count = filter_size * c_in * c_out;
+        const int rc = hpl_absmax(w, w_count, w_amax, stream);
+        if (rc != 0) return rc;
+        const long long chunks = n_tiles * n_kb_total * (tn * (TK / 8));
+        const unsigned img_blocks = (unsigned)((chunks + 255) / 256);
+        if (tn256)
+            weight_image16_kernel<256><<<img_blocks, 256, 0, s>>>(w, w_sf, w_sc, w_so, (int)filter_size, (int)c_in, (int)c_out, kb_per_tap, w_amax, image);
+        else if (wide)
+            weight_image16_kernel<128><<<img_blocks, 256, 0, s>>>(w, w_sf, w_sc, w_so, (int)filter_size, (int)c_in, (int)c_out, kb_per_tap, w_amax, image);
+        else
+            weight_image16_kernel<64><<<img_blocks, 256, 0, s>>>(w, w_sf, w_sc, w_so, (int)filter_size, (int)c_in, (int)c_out, kb_per_tap, w_amax, image);
+    }
     const long long steps = n_kb_total * (TK / 16);
     const long long m_tiles = (n_out_rows + TM - 1) / TM;
     if (tn256) {

@@ -22,6 +22,40 @@ DEFAULT_PRECISION = int(_os.environ.get("HPL_GEMM_PRECISION", "2"))
 _tc_workspace = {}
 
 
+# Weight images (pre-split, pre-laid-out fp16 hi/lo copies of a conv weight, built by two small kernels per call) are
+# kept per PARAMETER while its version counter is unchanged: in evaluation the weights never change, in training they
+# change once per optimisation step while every pair of the step reuses them.  Only module parameters are cached (the
+# owner travels as ``w._hpl_owner = (parameter, role)``); ad-hoc weight tensors are always re-imaged.
+WEIGHT_CACHE = True
+_weight_images = {}
+
+
+def _cached_workspace(w, nbytes, wide_rows):
+    """(workspace tensor, valid flag) for the weight view w; valid = the image inside is current."""
+    owner = getattr(w, "_hpl_owner", None)
+    if not WEIGHT_CACHE or owner is None:
+        return _workspace(w.device, nbytes), 0
+    import weakref
+    param, role = owner
+    key = (id(param), role, wide_rows, torch.cuda.current_stream(w.device).cuda_stream)
+    ent = _weight_images.get(key)
+    if ent is not None and ent[0]() is param and ent[1] == param._version and ent[2].numel() * 4 >= nbytes \
+            and ent[3] == (tuple(w.shape), tuple(w.stride()), w.data_ptr()):
+        return ent[2], 1
+    ws = torch.empty(nbytes // 4 + 4, dtype=torch.float32, device=w.device)
+    if len(_weight_images) > 4096:                      # parameters that died: drop their images
+        for k in [k for k, e in _weight_images.items() if e[0]() is None]:
+            del _weight_images[k]
+    _weight_images[key] = (weakref.ref(param), param._version, ws, (tuple(w.shape), tuple(w.stride()), w.data_ptr()))
+    return ws, 0
+
+
+def with_owner(view, param, role):
+    """Tag a weight view with the parameter it was derived from (enables the weight-image cache)."""
+    view._hpl_owner = (param, role)
+    return view
+
+
 def _workspace(device, nbytes):
     # rewritten by every call that uses it, so it is private to one (device, stream)
     key = (device.index, torch.cuda.current_stream(device).cuda_stream, nbytes)
@@ -232,16 +266,16 @@ def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_majo
                       w.data_ptr(), bias_ptr, act, out.data_ptr(), out.stride(0), int(out_channel_major),
                       ws.data_ptr(), x_amax.data_ptr(), _stream())
     elif precision == 2:
-        ws = _workspace(x.device, _lib.load().hpl_blur_gemm_f16_workspace(f, c, co))
         if x_amax is None:
             x_amax = absmax(x)
         if not _dense_permutation(w):
             w = w.contiguous()
+        ws, ws_valid = _cached_workspace(w, _lib.load().hpl_blur_gemm_f16_workspace(f, c, co), n_out_rows >= 8192)
         with _timed(tag):
             _lib.call("hpl_blur_gemm_f16_amax", x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, f, n_out_rows, c, co,
                       _base_ptr(w), w.stride(0), w.stride(1), w.stride(2),
                       bias_ptr, act, out.data_ptr(), out.stride(0), int(out_channel_major),
-                      ws.data_ptr(), x_amax.data_ptr(), out_amax.data_ptr() if out_amax is not None else None, _stream())
+                      ws.data_ptr(), ws_valid, x_amax.data_ptr(), out_amax.data_ptr() if out_amax is not None else None, _stream())
         out_amax = None
     elif precision == 1:
         ws = _workspace(x.device, _lib.load().hpl_blur_gemm_tc_workspace(f, c, co))

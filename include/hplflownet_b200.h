@@ -160,6 +160,9 @@ int hpl_blur_wgrad_p16(const void* in16, int64_t n_in_rows, const void* nbr, int
  *     (f, c, o) of the logical (F, C, Co) weight sits at w[f * w_sf + c * w_sc + o * w_so] inside one dense buffer of
  *     F * C * Co floats starting at w, so the reference's (Co, C, F, 1) conv weight (strides 1, F, C * F) and its
  *     transpose for the data gradient are consumed in place, without permuted copies.  All three 0 = contiguous.
+ *     workspace_valid != 0: `workspace` still holds the image this function built for the SAME weight values, shape,
+ *     strides and the same tile-width class (n_out_rows >= 8192 or not) -- the absmax + image kernels are skipped
+ *     (the binding keeps one workspace per parameter and tracks its version counter).
  *   hpl_normalize_rows_amax / hpl_cm_to_rows_amax: the same for the producers of a stack's first input.
  *   hpl_act_backward_stats: dz *= act'(y) (act NONE: dz untouched, y may be NULL), max|dz| -> amax, sum_v dz[v, :] ->
  *     colsum (+=, the convolution's bias gradient); amax / colsum may be NULL. */
@@ -167,7 +170,7 @@ int hpl_blur_gemm_f16_amax(const float* in, int64_t ld_in, int64_t n_in_rows, co
                            int64_t filter_size, int64_t n_out_rows, int64_t c_in, int64_t c_out,
                            const float* w, int64_t w_sf, int64_t w_sc, int64_t w_so, const float* bias, int act,
                            float* out, int64_t ld_out, int out_channel_major, void* workspace,
-                           const uint32_t* in_amax, uint32_t* out_amax, void* stream);
+                           int workspace_valid, const uint32_t* in_amax, uint32_t* out_amax, void* stream);
 int hpl_normalize_rows_amax(float* rows, int64_t ld, int64_t n_rows, int64_t channels, const float* wsum,
                             float* inv, uint32_t* amax, void* stream);
 int hpl_cm_to_rows_amax(const float* cm, int64_t ld_cm, int64_t n, int64_t channels, float* rows, int64_t ld,

@@ -190,3 +190,37 @@ def test_bcl_tma_engine_matches_default_engine(monkeypatch):
         res[engine] = [y.detach().clone(), f.grad.clone()] + [p.grad.clone() for p in mod.parameters()]
     for a, b in zip(res[4], res[2]):
         assert_close(a, b, "engine 4 vs engine 2")
+
+
+def test_weight_image_cache_follows_parameter_updates():
+    """The per-parameter weight-image cache (ops.WEIGHT_CACHE) must be invisible: same results as without it, and an
+    in-place parameter update (what an optimizer step does) must invalidate it."""
+    from hplflownet_b200 import ops
+    d = _lattice(2048, 9, 1.0)
+    torch.manual_seed(1)
+    mod = hpl.BilateralConvFlex(3, 1, 32, [32, 16], "cuda", use_bias=True, use_leaky=True, use_norm=True,
+                                do_splat=True, do_slice=True, last_relu=False, chunk_size=-1).to(DEV)
+    feat = torch.randn(1, 32, 2048, device=DEV)
+    bary, off, nbr = d["pc1_barycentric"].to(DEV), d["pc1_lattice_offset"].to(DEV), d["pc1_blur_neighbors"].to(DEV)
+
+    def run(cache):
+        ops.WEIGHT_CACHE = cache
+        f = feat.clone().requires_grad_(True)
+        y = mod(f, bary, off, nbr, bary, off)
+        y.sum().backward()
+        return y.detach().clone(), f.grad.clone()
+    try:
+        y0, g0 = run(True)
+        y1, g1 = run(True)                       # second call: images served from the cache
+        assert_close(y1, y0, "cached second call")        # (not bitwise: the splat's RED order varies)
+        assert_close(g1, g0, "cached second call, grad")
+        with torch.no_grad():
+            for p in mod.parameters():
+                p.mul_(1.5)                      # in-place: bumps the version counter
+        y2, g2 = run(True)
+        y3, g3 = run(False)
+        assert not torch.allclose(y2, y0)
+        assert_close(y2, y3, "after update, cached vs uncached")
+        assert_close(g2, g3, "grad after update, cached vs uncached")
+    finally:
+        ops.WEIGHT_CACHE = True

@@ -269,14 +269,13 @@ def run_ours(args):
     # before step i computes (what a pin_memory DataLoader does), so PCIe and the SMs overlap.
     copy_stream = torch.cuda.Stream(device=dev)
 
-    def upload():
-        with torch.cuda.stream(copy_stream):
-            t = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return t, ev
-
-    def e2e_run(n_steps):
+    def e2e_run(n_steps, host=host):
+        def upload():
+            with torch.cuda.stream(copy_stream):
+                t = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return t, ev
         nxt = upload()
         for i in range(n_steps):
             t, ev = nxt
@@ -304,13 +303,25 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d2h = 4 + sum(p.numel() * 4 for p in params)
+    # supplementary: the same loop with the index tables in the native int32 format (the module accepts both; the
+    # reference's DataLoader ships int64, which is what the headline e2e uploads)
+    host32 = dict(host)
+    for k in ("lattice_offset", "blur_neighbors"):
+        host32[k] = host[k].to(torch.int32).pin_memory()
+    e2e_run(3, host32)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_run(e2e_steps, host32)
+    barrier()
+    e2e32_s = time.perf_counter() - t0
+    h2d32 = sum(v.numel() * v.element_size() for v in host32.values())
 
     # ---- secondary, all ranks: data-parallel HPLFlowNet training step (BASELINE configs[4])
     ops.WEIGHT_CACHE = True
     train = train_leg(dev, rank, world)
 
     # ---- max over ranks
-    ms, e2e_s = sharding.max_over_ranks([ms, e2e_s], device=dev)
+    ms, e2e_s, e2e32_s = sharding.max_over_ranks([ms, e2e_s, e2e32_s], device=dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -356,6 +367,7 @@ def run_ours(args):
 
     cpu = cpu_baseline_leg()
     lattice = lattice_leg(dev)
+    corr = corr_leg(dev)
     model_fwd = model_leg(dev)
 
     line = {
@@ -371,8 +383,11 @@ def run_ours(args):
                    "weight_images": "rebuilt on every call in the timed loops (cache disabled)"},
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "clouds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps},
-        "gpu_launches": launches, "clocks": clocks, "lattice_build": lattice, "model_forward": model_fwd,
+                "steps": e2e_steps,
+                "int32_tables": {"value": sharding.job_throughput(B * e2e_steps, world, e2e32_s), "unit": "clouds/s",
+                                 "h2d_bytes_per_step": h2d32,
+                                 "note": "same loop, index tables uploaded in the native int32 format"}},
+        "gpu_launches": launches, "clocks": clocks, "lattice_build": lattice, "correlation": corr, "model_forward": model_fwd,
         "train_step": train,
     }
     print(json.dumps(line))
@@ -489,6 +504,56 @@ def model_leg(dev):
                 "pairs_per_s": 1e3 / out["build_plus_forward_ms"], "output_finite": bool(torch.isfinite(y).all()),
                 "note": "reference CPU forward: 13.8 s/pair + 4.1-4.9 s lattice build (SURVEY §6, 8 vCPU)"})
     return out
+
+
+def corr_leg(dev):
+    """Secondary number (BASELINE configs[2]): BilateralCorrelationFlex(3, 1, 1, 64, [32, 32], [64, 64], prev_corr_dim=64)
+    forward + backward on two 8192-point clouds at scale 1.0, tables from the GPU lattice builder."""
+    import torch
+    import hplflownet_b200 as hpl
+    from hplflownet_b200.synthetic import frustum_pair
+    from hplflownet_b200.transforms import GenerateDataUnsymmetric
+
+    class A:
+        dim = 3
+        scales_filter_map = [[SCALE, 1, 1, 1]]
+    gen = GenerateDataUnsymmetric(A(), device=dev, index_dtype=torch.int32)
+    pc1, pc2 = frustum_pair(N_POINTS, 11)
+    a, b = torch.from_numpy(pc1.T.copy()).to(dev), torch.from_numpy(pc2.T.copy()).to(dev)
+    d = gen.build(a, b)[0]
+    h1, h2 = int(d["pc1_hash_cnt"]), int(d["pc2_hash_cnt"])
+    torch.manual_seed(0)
+    mod = hpl.BilateralCorrelationFlex(3, 1, 1, CHANNELS, [32, 32], [64, 64], "cuda", use_bias=True, use_leaky=True,
+                                       use_norm=True, prev_corr_dim=CHANNELS, last_relu=False, chunk_size=-1).to(dev)
+    f1 = torch.randn(1, CHANNELS, h1, device=dev, requires_grad=True)
+    f2 = torch.randn(1, CHANNELS, h2, device=dev, requires_grad=True)
+    prev = torch.randn(1, CHANNELS, N_POINTS, device=dev, requires_grad=True)
+    args = (d["pc1_barycentric"][None], d["pc1_lattice_offset"][None], d["pc1_corr_indices"][None],
+            d["pc2_corr_indices"][None], h1, h2)
+    gy = None
+
+    def step():
+        nonlocal gy
+        for t in (f1, f2, prev, *mod.parameters()):
+            t.grad = None
+        y = mod(f1, f2, prev, *args)
+        if gy is None:
+            gy = torch.randn_like(y)
+        y.backward(gy)
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    e0.record()
+    for _ in range(reps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {"workload": "BilateralCorrelationFlex(3,1,1,64,[32,32],[64,64],prev_corr_dim=64) fwd+bwd, 8192+8192 pts, scale 1.0",
+            "ms_per_pair": ms, "pairs_per_s": 1e3 / ms, "H1": h1, "H2": h2,
+            "note": "the reference materialises 172.8 KB per vertex for this layer (bnn_flow.py:189-199)"}
 
 
 def lattice_leg(dev):

@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libhplflownet_b200.so")
+LIB_PATH = os.environ.get("HPL_LIB_PATH") or os.path.join(_PKG, "libhplflownet_b200.so")   # (override: timing experiments)
 
 i64, i32, vp, cint = ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int
 

@@ -72,6 +72,14 @@ __device__ __forceinline__ void scale_from_amax(uint32_t bits, float& scale, flo
 
 // 4 consecutive fp32 -> 4 hi halves + 4 lo halves (2 x b32 each)
 __device__ __forceinline__ void split4h(const float4 a, float inv_s, uint32_t* hi, uint32_t* lo) {
+#ifdef HPL_EXP_NOSPLIT                      // timing experiment only (wrong numbers): one conversion, no residual arithmetic
+    {
+        const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+        hi[0] = lo[0] = *reinterpret_cast<const uint32_t*>(&h0);
+        hi[1] = lo[1] = *reinterpret_cast<const uint32_t*>(&h1);
+        return;
+    }
+#endif
     const float x[4] = {a.x * inv_s, a.y * inv_s, a.z * inv_s, a.w * inv_s};
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -239,7 +247,11 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
             const bool live = c + 4 * c16 < c_in;
 #pragma unroll
             for (int b = 0; b < NB; ++b)
+#ifdef HPL_EXP_NOLOAD                       // timing experiment only: no gathered loads
+                dst[b] = make_float4((float)c, 1.f, 2.f, (float)b);
+#else
                 dst[b] = (rowp[b] != nullptr && live) ? __ldg(reinterpret_cast<const float4*>(rowp[b] + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#endif
             ++issued;
             if (++kt_i == kb_per_tap) { kt_i = 0; ++tap_i; }
         };

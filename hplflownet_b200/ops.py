@@ -193,10 +193,6 @@ def _dense_permutation(w):
     return True
 
 
-def _base_ptr(w):
-    return w.data_ptr()
-
-
 def tc_path(c_in, precision=None):
     """True when the tensor-core kernels (which can fold ``row_scale``) will run for this operand."""
     return (DEFAULT_PRECISION if precision is None else precision) >= 1 and c_in % 4 == 0
@@ -273,7 +269,7 @@ def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_majo
         ws, ws_valid = _cached_workspace(w, _lib.load().hpl_blur_gemm_f16_workspace(f, c, co), n_out_rows >= 8192)
         with _timed(tag):
             _lib.call("hpl_blur_gemm_f16_amax", x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, f, n_out_rows, c, co,
-                      _base_ptr(w), w.stride(0), w.stride(1), w.stride(2),
+                      w.data_ptr(), w.stride(0), w.stride(1), w.stride(2),
                       bias_ptr, act, out.data_ptr(), out.stride(0), int(out_channel_major),
                       ws.data_ptr(), ws_valid, x_amax.data_ptr(), out_amax.data_ptr() if out_amax is not None else None, _stream())
         out_amax = None

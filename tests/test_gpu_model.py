@@ -120,3 +120,64 @@ def test_shallow_model_forward_and_backward():
             assert_close_grad(p.grad, state[name].grad, "grad " + name)
             checked += 1
     assert checked >= 60
+
+
+def test_model_forward_baseline_size_matches_float64_oracle():
+    """BASELINE configs[3]: full HPLFlowNet forward on an 8192+8192-point FlyingThings3D-shaped pair (all seven scales,
+    the 256-wide contraction tiles and the K-split path are exercised here: H = 26 k / 35 k on the two finest levels),
+    against the oracle composition evaluated in float64 on the host."""
+    from hplflownet_b200.synthetic import frustum_pair
+    from oracle import hplflownet as OM
+    from oracle import lattice as OL
+    pc1, pc2 = frustum_pair(8192, 7)
+    model = name_keyed_init_(HPLFlowNet(ModelArgs()), 5)
+    state = {k: (v.detach().clone().double() if v.is_floating_point() else v.clone()) for k, v in model.state_dict().items()}
+    gd_np = OL.generate(pc1, pc2, ModelArgs.scales_filter_map)
+    gd_ref = [{k: (torch.from_numpy(v)[None] if not isinstance(v, int) else v) for k, v in d.items()} for d in gd_np]
+    gd_ref = [{k: (v.double() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in d.items()} for d in gd_ref]
+    p1, p2 = [torch.from_numpy(np.ascontiguousarray(p.T))[None].double() for p in (pc1, pc2)]
+    with torch.no_grad():
+        want = OM.forward(state, p1, p2, gd_ref)
+
+    model = model.cuda().eval()
+    gen = GenerateDataUnsymmetric(ModelArgs())
+    a, b, sf, gd = gen([pc1, pc2, pc2 - pc1])
+    for k in range(7):                       # the GPU builder's tables equal the oracle's (bit-exact contract)
+        assert int(gd[k]["pc1_hash_cnt"]) == int(gd_np[k]["pc1_hash_cnt"])
+    with torch.no_grad():
+        out = model(a[None], b[None], collate_batch1(gd))
+    assert out.shape == (1, 3, 8192)
+    assert_close(out, want, "flow at BASELINE size")
+
+
+def test_model_backward_baseline_size_matches_float64_oracle():
+    """BASELINE configs[4] numerics: loss and every parameter gradient of one 8192+8192-point pair (EPE3D loss) against
+    the oracle's autograd in float64 -- the wide weight-gradient tiles and split-K data gradients at their real sizes."""
+    from hplflownet_b200.synthetic import frustum_pair
+    from oracle import hplflownet as OM
+    from oracle import lattice as OL
+    from tests._util import assert_close_grad
+    pc1, pc2 = frustum_pair(8192, 9)
+    model = name_keyed_init_(HPLFlowNet(ModelArgs()), 6)
+    state = {k: (v.detach().clone().double().requires_grad_(True) if v.is_floating_point() else v.clone())
+             for k, v in model.state_dict().items()}
+    gd_np = OL.generate(pc1, pc2, ModelArgs.scales_filter_map)
+    gd_ref = [{k: (torch.from_numpy(v)[None] if not isinstance(v, int) else v) for k, v in d.items()} for d in gd_np]
+    gd_ref = [{k: (v.double() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in d.items()} for d in gd_ref]
+    p1, p2 = [torch.from_numpy(np.ascontiguousarray(p.T))[None].double() for p in (pc1, pc2)]
+    target = torch.from_numpy(np.ascontiguousarray((pc2 - pc1).T))[None].double()
+    loss_ref = torch.norm(OM.forward(state, p1, p2, gd_ref) - target, p=2, dim=1).mean()
+    loss_ref.backward()
+
+    model = model.cuda().train()
+    gen = GenerateDataUnsymmetric(ModelArgs())
+    a, b, sf, gd = gen([pc1, pc2, pc2 - pc1])
+    loss = torch.norm(model(a[None], b[None], collate_batch1(gd)) - sf[None], p=2, dim=1).mean()
+    loss.backward()
+    assert_close(loss.detach(), loss_ref.detach(), "loss")
+    checked = 0
+    for name, p in model.named_parameters():
+        if p.grad is not None:
+            assert_close_grad(p.grad, state[name].grad, "grad " + name)
+            checked += 1
+    assert checked >= 100

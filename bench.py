@@ -201,6 +201,8 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from hplflownet_b200 import sharding
+    numa_node = sharding.bind_to_gpu_numa_node(local) if world > 1 else None      # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.clouds
@@ -380,7 +382,8 @@ def run_ours(args):
                    "l2_policy": "inputs larger than L2 (working set %.0f MB per step)" % (
                        4e-6 * (2 * n_tot * CHANNELS + 2 * h_tot * CHANNELS)),
                    "index_dtype": "int64 (reference format)",
-                   "weight_images": "rebuilt on every call in the timed loops (cache disabled)"},
+                   "weight_images": "rebuilt on every call in the timed loops (cache disabled)",
+                   "numa_node_rank0": numa_node},
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "clouds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps,

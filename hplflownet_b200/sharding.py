@@ -35,3 +35,30 @@ def max_over_ranks(values, device="cpu"):
 def job_throughput(units_per_rank, world_size, seconds_max_over_ranks):
     """Whole-job units/s: all ranks' units divided by the slowest rank's time."""
     return units_per_rank * world_size / seconds_max_over_ranks
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process (and therefore the pinned host buffers it allocates next: first-touch placement) to the CPUs
+    of the NUMA node its GPU hangs off.  With one process per GPU on a multi-socket host this keeps every rank's
+    host-to-device traffic on its own socket.  Best effort: returns the node id, or None when the topology cannot be
+    read (no sysfs entry, single node, insufficient rights)."""
+    import os
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:                                            # noqa: BLE001 -- topology is optional information
+        return None

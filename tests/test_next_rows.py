@@ -54,3 +54,21 @@ def test_checkpoint_roundtrip_reference_layout(tmp_path):
             assert torch.equal(a, b), k
         # a bare (un-prefixed) state_dict loads as well
         other.load_state_dict(C.strip_module_prefix(model.state_dict()), strict=True)
+
+
+def test_dense_permutation_detection():
+    """ops._dense_permutation decides whether a weight view can be handed to the strided kernel as is."""
+    from hplflownet_b200 import ops
+    w = torch.randn(6, 5, 4)                                   # "conv layout" (Co, C, F)
+    assert ops._dense_permutation(w)
+    assert ops._dense_permutation(w.permute(2, 1, 0))          # (F, C, Co) view: forward operand
+    assert ops._dense_permutation(w.permute(2, 1, 0).transpose(1, 2))   # (F, Co, C): data-gradient operand
+    assert ops._dense_permutation(torch.randn(1, 5, 4).permute(0, 2, 1))   # size-1 dims carry arbitrary strides
+    assert not ops._dense_permutation(w[:, :, ::2])            # holes
+    assert not ops._dense_permutation(w[:3])  or w[:3].is_contiguous()     # a leading slice is still dense
+    assert not ops._dense_permutation(w.expand(2, 6, 5, 4)[0][:, :, :2])   # partial last dim
+
+
+def test_numa_binding_is_best_effort_without_gpu():
+    from hplflownet_b200 import sharding
+    assert sharding.bind_to_gpu_numa_node(0) is None or isinstance(sharding.bind_to_gpu_numa_node(0), int)

@@ -50,6 +50,13 @@ def _cached_workspace(w, nbytes, wide_rows):
     return ws, 0
 
 
+def invalidate_weight_cache():
+    """Drop every cached weight image.  The cache follows ``Parameter._version``, which in-place updates through
+    ``param.data`` (old-style optimizers, manual clipping) do NOT bump: call this after such an update.
+    ``train.train_step`` calls it after every optimizer step regardless."""
+    _weight_images.clear()
+
+
 def with_owner(view, param, role):
     """Tag a weight view with the parameter it was derived from (enables the weight-image cache)."""
     view._hpl_owner = (param, role)

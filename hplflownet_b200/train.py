@@ -51,4 +51,6 @@ def train_step(model, optimizer, generator, pairs, collate):
         total = loss.detach() if total is None else total + loss.detach()
     allreduce_mean_grads_(list(model.parameters()))
     optimizer.step()
+    from . import ops
+    ops.invalidate_weight_cache()            # the step changed every weight (belt and braces next to the version check)
     return total

@@ -76,6 +76,7 @@ def _workspace(device, nbytes):
 # bench.py sets this to a list to collect (tag, start_event, end_event) around the contraction
 # kernels (CUDA events on the launching stream); None = no instrumentation.
 PROFILE_GEMM = None
+PROFILE_ROWS = False            # also time the splat / slice kernels (bench.py enables it for a separate, untimed pass)
 
 
 class _timed:
@@ -83,13 +84,14 @@ class _timed:
         self.tag = tag
 
     def __enter__(self):
-        if PROFILE_GEMM is not None:
+        self.on = PROFILE_GEMM is not None and (PROFILE_ROWS or self.tag not in ("scatter", "gather"))
+        if self.on:
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e1 = torch.cuda.Event(enable_timing=True)
             self.e0.record()
 
     def __exit__(self, *a):
-        if PROFILE_GEMM is not None:
+        if self.on:
             self.e1.record()
             PROFILE_GEMM.append((self.tag, self.e0, self.e1))
 
@@ -129,8 +131,9 @@ def scatter_rows(x, bary, off, n_rows, want_wsum):
     c, n = x.shape
     rows = alloc_rows(n_rows, c, x.device, zero=True)
     wsum = torch.zeros(n_rows, dtype=torch.float32, device=x.device) if want_wsum else None
-    _lib.call("hpl_scatter_rows", x.data_ptr(), bary.data_ptr(), off.data_ptr(), i64, n, c,
-              rows.data_ptr(), rows.stride(0), wsum.data_ptr() if want_wsum else None, _stream())
+    with _timed("scatter"):
+        _lib.call("hpl_scatter_rows", x.data_ptr(), bary.data_ptr(), off.data_ptr(), i64, n, c,
+                  rows.data_ptr(), rows.stride(0), wsum.data_ptr() if want_wsum else None, _stream())
     return rows, wsum
 
 
@@ -211,9 +214,10 @@ def gather_rows(rows, channels, bary, off, scale=None, bias=None):
     off, i64 = _idx(off, "off")
     n = bary.size(-1)
     y = torch.empty((channels, n), dtype=torch.float32, device=rows.device)
-    _lib.call("hpl_gather_rows", rows.data_ptr(), rows.stride(0), bary.data_ptr(), off.data_ptr(), i64,
-              scale.data_ptr() if scale is not None else None,
-              bias.data_ptr() if bias is not None else None, n, channels, y.data_ptr(), _stream())
+    with _timed("gather"):
+        _lib.call("hpl_gather_rows", rows.data_ptr(), rows.stride(0), bary.data_ptr(), off.data_ptr(), i64,
+                  scale.data_ptr() if scale is not None else None,
+                  bias.data_ptr() if bias is not None else None, n, channels, y.data_ptr(), _stream())
     return y
 
 

@@ -56,13 +56,28 @@ SIGNATURES = {
     "hpl_lattice_neighbors": [vp, vp, i64, vp, vp, vp, i64, vp, i64, vp, cint, i64, vp],
     "hpl_lattice_corr_table": [vp, vp, i64, vp, vp, vp, i64, vp, i64, vp, i64, vp, cint, i64, vp],
     "hpl_lattice_next_points": [vp, i64, ctypes.c_float, vp, vp],
+    "hpl_plan_tiles": [i64],
+    "hpl_plan_umax": [],
+    "hpl_plan_offset": [i64, cint],
+    "hpl_plan_bytes": [i64],
+    "hpl_plan_build": [vp, cint, i64, i64, i64, vp, vp, vp, vp],
+    "hpl_plan_order_workspace": [i64],
+    "hpl_plan_order": [vp, cint, i64, i64, vp, cint, vp, vp, vp, vp],
+    "hpl_h16b_bytes": [i64, i64],
+    "hpl_h16b_split": [vp, i64, i64, i64, vp, vp, vp, vp],
+    "hpl_conv5_workspace": [i64],
+    "hpl_conv5_supported": [i64, i64, i64],
+    "hpl_conv5": [vp, vp, i64, i64, i64, i64, vp, i64, i64, i64, vp, vp, cint, vp, i64, vp, cint, vp, vp, vp],
+    "hpl_wgrad5": [vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp],
     "hpl_fill_zero": [vp, i64, vp],
     "hpl_fill_i32": [vp, i64, i32, vp],
 }
 
 
 RETURNS_I64 = {"hpl_lattice_table_capacity", "hpl_lattice_scan_blocks", "hpl_blur_gemm_tc_workspace",
-               "hpl_blur_gemm_f16_workspace", "hpl_split16_bytes", "hpl_h16_bytes", "hpl_blur_gemm_tma_workspace"}   # sizes, not status codes
+               "hpl_blur_gemm_f16_workspace", "hpl_split16_bytes", "hpl_h16_bytes", "hpl_blur_gemm_tma_workspace",
+               "hpl_plan_tiles", "hpl_plan_umax", "hpl_plan_offset", "hpl_plan_bytes", "hpl_plan_order_workspace",
+               "hpl_h16b_bytes", "hpl_conv5_workspace", "hpl_conv5_supported"}   # sizes, not status codes
 
 # kernels enqueued per call (for bench.py's gpu_launches claim)
 LAUNCHES = {
@@ -73,6 +88,7 @@ LAUNCHES = {
     "hpl_corr_gather": 1, "hpl_corr_scatter": 1, "hpl_column_sums": 1,
     "hpl_lattice_init_range": 1, "hpl_lattice_points": 1, "hpl_lattice_insert": 6,
     "hpl_lattice_neighbors": 1, "hpl_lattice_corr_table": 1, "hpl_lattice_next_points": 1,
+    "hpl_plan_build": 1, "hpl_h16b_split": 1, "hpl_conv5": 3, "hpl_wgrad5": 1,
 }
 launch_count = 0
 

@@ -1,0 +1,914 @@
+// Engine 5: the lattice convolution (blur forward / data gradient, models/bilateralNN.py:198-221) as a persistent
+// tcgen05 kernel that loads every DISTINCT neighbour row of a 128-vertex tile ONCE.
+//
+// Engines 2 / 4 gather F = 15 rows per vertex straight from L2 (1.2 GB of L2 -> SM traffic per cfg2 x 32 launch, the
+// measured floor of those designs).  Here a per-lattice tile plan (plan.cu) lists, for every tile of 128 spatially
+// coherent vertices, the ~320 distinct rows its 15 x 128 table entries reference; the kernel
+//   1. stages those rows once in shared memory (cp.async, one 128-byte line per quarter warp, double-buffered: the
+//      next phase's rows arrive while the current phase computes),
+//   2. builds the UMMA A operand of every tap by shared -> shared copies (LDS.128 / STS.128, conflict-free on both
+//      sides: a quarter warp moves one staged row into 8 different bank groups of the K-major no-swizzle layout),
+//   3. runs 3xFP16 as TWO MMAs per K step instead of three: the weight tile holds [W_hi ; W_lo] as 128 N rows, so
+//      x_hi . [W_hi | W_lo] is one M128 N128 K16 instruction (main term in columns 0-63, cross term in 64-127) and
+//      x_lo . W_hi (N = 64) accumulates onto the cross columns.  The A operand is read from shared memory once for two
+//      products (the SM's 128 B / clk shared-memory port is the binding resource of this kernel).
+// Operands arrive pre-split ("h16b" image: per row and 32-channel block, 32 fp16 hi | 32 fp16 lo = one 128-byte line;
+// x / s = hi + lo * 2^-11, s a per-tensor power of two, see gemm_tc16.cu); producers of lattice rows write that image
+// directly (rows.cu), so nothing is converted here.
+//
+// Work decomposition: CTA = one SM, contiguous range of tiles; phase = (tile, 32-channel block); stage = two taps of a
+// phase (A: 2 x 16.1 KB, W: 2 x 8 KB), ring of 2.  Warps: 0-7 copy (U loads + A stage copies), 8 MMA issuer (one
+// thread), 9 weight stream (cp.async.bulk, one 16 KB copy per stage), 10-13 epilogue (tcgen05.ld, bias, activation,
+// fp32 row stores in the reference's vertex order, max|out| statistic) overlapped with the next tile through
+// double-buffered TMEM accumulators.
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+
+extern "C" int64_t hpl_plan_offset(int64_t n_rows, int which);
+extern "C" int64_t hpl_plan_tiles(int64_t n_rows);
+
+namespace {
+
+using namespace tc;
+
+constexpr int TM = 128;
+constexpr int kTaps = 16;                        // taps the plan's index block holds (F = 15)
+constexpr int kUmax = 464;                       // distinct rows per tile (plan.cu)
+constexpr int kURow = 128;                       // staged bytes per row and phase: 32 ch hi | 32 ch lo
+constexpr int kUBuf = (kUmax + 1) * kURow;       // + the zero row (slot kUmax)
+constexpr uint32_t kA_LBO = TM * 16 + 16;        // 2064: K-chunk stride of an A plane (129 x 16 B: odd -> conflict-free)
+constexpr int kAPlane = 4 * kA_LBO;              // 8256: hi (or lo) plane of one tap, 32 channels
+constexpr int kATap = 2 * kAPlane;               // 16512
+constexpr int kAStage = 2 * kATap;               // two taps
+constexpr uint32_t kB_LBO = 128 * 16;            // weight tile: 128 N rows ([W_hi ; W_lo]) x 32 K
+constexpr int kBTap = 4 * kB_LBO;                // 8192
+constexpr int kBStage = 2 * kBTap;
+constexpr int kStages = 2;
+constexpr int kIdxBuf = kTaps * TM * 2;          // 4096 B of uint16 slots
+constexpr int kCopyWarps = 8, kCopyThreads = kCopyWarps * 32;      // weight-gradient kernel: one copy group
+constexpr int kMmaWarp = 8, kWWarp = 9;
+constexpr int kThreads = 14 * 32;
+// forward kernel: TWO copy groups of 8 warps, group g fills ring slot g (alternate stages), so one group's fixed latencies
+// (barrier wake-up, proxy fence) overlap the other group's shared-memory traffic
+constexpr int kC5CopyWarps = 16, kC5CopyThreads = kC5CopyWarps * 32;
+constexpr int kC5MmaWarp = 16, kC5WWarp = 17;                       // warps 18-21: epilogue
+constexpr int kC5Threads = 22 * 32;
+constexpr int kC5UIters = (kUmax * 8 + kC5CopyThreads - 1) / kC5CopyThreads;   // 8 row-chunk copies per thread and phase
+constexpr int kSmem = 2 * kUBuf + kStages * (kAStage + kBStage) + 2 * kIdxBuf + 1024;
+constexpr int kUIters = (kUmax * 8 + kCopyThreads - 1) / kCopyThreads;      // 15 row-chunk copies per thread and phase
+constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
+static_assert(kSmem <= 232448, "shared memory budget");
+
+__device__ __forceinline__ void scale_from_amax(uint32_t bits, float& scale, float& inv_scale) {
+    int e = (int)((bits >> 23) & 0xff) - 127;
+    if (bits == 0) e = 13;
+    int se = e - 13;
+    se = se < -100 ? -100 : (se > 100 ? 100 : se);
+    scale = __uint_as_float((uint32_t)(se + 127) << 23);
+    inv_scale = __uint_as_float((uint32_t)(127 - se) << 23);
+}
+
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn((a - f.x) * kLoScale, (b - f.y) * kLoScale);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// bounded wait: a barrier that never flips (descriptor / byte-count bug) traps after ~4 s instead of hanging the GPU.
+// The suspend-time hint lets the thread sleep in hardware until the phase completes.
+__device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    unsigned long long t0 = 0;
+    for (uint32_t tries = 0; !done; ++tries) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity), "r"(0x100000u)
+            : "memory");
+        if (!done && tries >= 64) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) __trap();
+        }
+    }
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------- h16b image
+// x (n_rows, ld) fp32 vertex-major -> (n_rows, CB) lines of [32 hi | 32 lo] halves, CB = ceil(C / 32); channels beyond C
+// are zero.  norm != nullptr: x[v, :] is first multiplied by 1 / (norm[v] + 1e-5) (density normalisation,
+// bilateralNN.py:185-186, fused into the split).  One thread = 8 channels of one row.
+__global__ void h16b_split_kernel(const float* __restrict__ x, long long ld, long long n_rows, int channels, int cb_count,
+                                  const float* __restrict__ norm, const uint32_t* __restrict__ amax, uint4* __restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cpr = cb_count * 4;                                         // 8-channel groups per row
+    if (t >= n_rows * cpr) return;
+    const long long row = t / cpr;
+    const int g = (int)(t - row * cpr);
+    const int c0 = g * 8;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    const float* p = x + row * ld + c0;
+    if (c0 + 8 <= channels) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (c0 + i < channels) v[i] = __ldg(p + i);
+    }
+    float s, inv_s;
+    scale_from_amax(__ldg(amax), s, inv_s);
+    if (norm != nullptr) {
+        const float r = 1.0f / (__ldg(norm + row) + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] *= r;                             // same rounding as normalize_rows_kernel
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split2(v[2 * i] * inv_s, v[2 * i + 1] * inv_s, hi[i], lo[i]);
+    // line (row, cb = g / 4): 8 chunks of 16 B -- hi chunks 0..3, lo chunks 4..7
+    uint4* dst = out + (row * cb_count + (g >> 2)) * 8 + (g & 3);
+    dst[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    dst[4] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// ---------------------------------------------------------------------------------------- weight image
+// w[f, c, o] (strided) -> per (cb, stage = tap pair): two 8 KB tiles; tile rows n = 0..127 are [W_hi(o = n) ; W_lo(o = n - 64)],
+// K = 32 channels of block cb, K-major no-swizzle: chunk kc at kc * 2048 + (n / 8) * 128 + (n % 8) * 16.
+// tap_map (may be NULL): image tap g holds source tap tap_map[g] (the data gradient uses the mirrored tap).
+__global__ void weight_image5_kernel(const float* __restrict__ w, long long w_sf, long long w_sc, long long w_so, int filter_size,
+                                     int c_in, int c_out, int cb_count, const int* __restrict__ tap_map,
+                                     const uint32_t* __restrict__ w_amax, uint8_t* __restrict__ image) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)cb_count * kTaps * 64 * 4;          // (cb, tap, o, kc)
+    if (t >= total) return;
+    const int o = (int)(t & 63);
+    const int kc = (int)((t >> 6) & 3);
+    const int tap = (int)((t >> 8) & (kTaps - 1));
+    const int cb = (int)(t >> 12);
+    float s, inv_s;
+    scale_from_amax(*w_amax, s, inv_s);
+    const int f = tap < filter_size ? (tap_map != nullptr ? tap_map[tap] : tap) : -1;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float a[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int c = cb * 32 + kc * 8 + 2 * i + j;
+            a[j] = (f >= 0 && c < c_in && o < c_out) ? __ldg(w + f * w_sf + c * w_sc + o * w_so) * inv_s : 0.f;
+        }
+        split2(a[0], a[1], hi[i], lo[i]);
+    }
+    uint8_t* tile = image + ((long long)cb * kTaps + tap) * kBTap;
+    uint8_t* dst = tile + kc * kB_LBO + (o >> 3) * 128 + (o & 7) * 16;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(dst + 64 * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);          // rows 64..127
+}
+
+// ---------------------------------------------------------------------------------------- the kernel
+struct Conv5Args {
+    const uint8_t* in16;          // h16b image of the input rows
+    const uint8_t* w_image;
+    const int* tile_rows;         // plan
+    const int* n_uniq;
+    const int* uniq;
+    const unsigned short* local;
+    const float* bias;
+    float* out;
+    const uint32_t* in_amax;
+    const uint32_t* w_amax;
+    uint32_t* out_amax;
+    long long ld_out;
+    int n_tiles, cb_count, filter_size, c_out, act, n_main, steps_total;
+    long long* trace;             // timing experiments: clock64 stamps of CTA 0 (HPL_CONV5_TRACE), 8 per stage
+    int dbg;                      // timing experiments (HPL_CONV5_DBG): 1 no A copies, 2 no MMAs, 4 no W loads, 8 no U loads, 16 no stores
+};
+
+// F = taps processed (15: HPLFlowNet's r = 1 neighbourhood; 16: any other count, padded with zero taps)
+template <int F>
+__global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * kStages + 2 + 4];
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t u_base = smem_base;                                   // 2 x kUBuf
+    const uint32_t a_base = u_base + 2 * kUBuf;                          // kStages x kAStage
+    const uint32_t b_base = a_base + kStages * kAStage;                  // kStages x kBStage
+    const uint32_t idx_base = b_base + kStages * kBStage;                // 2 x kIdxBuf
+    const uint32_t bar0 = smem_u32(bars);
+    const uint32_t full = bar0, empty = full + 8 * kStages, ufull = empty + 8 * kStages;
+    const uint32_t acc_full = ufull + 16, acc_empty = acc_full + 16;
+
+    const int per = (p.n_tiles + gridDim.x - 1) / gridDim.x;
+    const int t_begin = blockIdx.x * per;
+    const int t_end = min(p.n_tiles, t_begin + per);
+    const int n_my = max(0, t_end - t_begin);
+    const int CB = p.cb_count;
+    constexpr int NP = (F + 1) / 2;                                      // stages per phase (two taps each)
+    static_assert(NP % 2 == 0 && kStages == 2, "stage s of a phase uses ring slot s & 1");
+    const int acc_cols = p.n_main * 128;                                 // TMEM columns of one accumulator set
+    const int acc_stages = 2 * acc_cols <= 512 ? 2 : 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&bars[s], kCopyWarps + 1); mbar_init(&bars[kStages + s], 1); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bars[2 * kStages + s], kC5CopyThreads);
+            mbar_init(&bars[2 * kStages + 2 + s], 1);
+            mbar_init(&bars[2 * kStages + 4 + s], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == kC5MmaWarp) tmem_alloc(&tmem_slot, 512);
+    // zero rows of both U buffers (slot kUmax): never overwritten (a tile stages at most kUmax rows)
+    if (threadIdx.x < 16) {
+        const uint32_t z = u_base + (threadIdx.x >> 3) * kUBuf + kUmax * kURow + (threadIdx.x & 7) * 16;
+        sts128(z, 0, 0, 0, 0);
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_d = tmem_slot;
+
+    if (warp < kC5CopyWarps) {
+        // ------------------------------------------------------------------ copy warps
+        // Their instruction stream paces the kernel (a first version with run-time tap / modulo tests ran ~500 dependent
+        // instructions per warp and stage: 2600 cycles per stage with everything else switched off), so everything is a
+        // compile-time schedule over per-thread constants: per stage 8 slot loads, 8 LDS.128, 8 STS.128 per thread.
+        const int tid = threadIdx.x;
+        const int grp = tid >> 8;                                        // copy group = ring slot it fills
+        const int gt = tid & 255;
+        const int c8 = gt & 7;                                           // 16-byte chunk of a 128-byte line
+        const int rg = gt >> 3;                                          // 0..31: row within a group of 32
+        const long long row_bytes = (long long)CB * kURow;
+        const int n_phases = n_my * CB;
+        const uint32_t src_off = c8 * 16;
+        const uint32_t idx_off = rg * 2;                                 // + (tap * 128 + q * 32) * 2
+        // A-stage position of (row = q * 32 + rg, chunk c8): + tap_l * kATap + q * 512
+        const uint32_t abd = a_base + grp * kAStage + (c8 >> 2) * kAPlane + (c8 & 3) * kA_LBO + (rg >> 3) * 128 + (rg & 7) * 16;
+        const uint8_t* in_thread = p.in16 + src_off;
+        const uint32_t full_g = full + 8 * grp, empty_g = empty + 8 * grp;
+
+        // U rows are loaded by all 512 threads: thread -> rows (tid >> 3) + i * 64
+        int urow[kC5UIters];
+        auto fetch_rows = [&](int k) {                                   // row ids of tile k (0-based in this CTA's range)
+            const int t = t_begin + k;
+            const int n = __ldg(p.n_uniq + t);
+            const int* up = p.uniq + (long long)t * kUmax + (tid >> 3);
+#pragma unroll
+            for (int i = 0; i < kC5UIters; ++i)
+                urow[i] = (tid >> 3) + i * (kC5CopyThreads / 8) < min(n, kUmax) ? __ldg(up + i * (kC5CopyThreads / 8)) : -1;
+        };
+        auto load_idx_block = [&](int k) {                               // the tile's index block: 256 chunks of 16 B
+            if (tid < 256)
+                cp_async16(idx_base + (k & 1) * kIdxBuf + tid * 16,
+                           reinterpret_cast<const uint8_t*>(p.local) + ((long long)(t_begin + k) * (kTaps * TM)) * 2 + tid * 16);
+        };
+        // rows i0 .. i0+3 of this thread's list for channel block cb into U buffer `ub`
+        auto load_rows = [&](uint32_t ub, int cb, int i0) {
+            const uint8_t* src = in_thread + cb * kURow;
+            const uint32_t dst = ub + (tid >> 3) * kURow + src_off;
+#pragma unroll
+            for (int i = i0; i < i0 + 4; ++i)
+                if (i < kC5UIters && urow[i] >= 0 && !(p.dbg & 8))
+                    cp_async16(dst + i * (kC5CopyThreads / 8) * kURow, src + (long long)urow[i] * row_bytes);
+        };
+
+        if (n_phases > 0) {
+            fetch_rows(0);
+            load_idx_block(0);
+#pragma unroll
+            for (int i0 = 0; i0 < kC5UIters; i0 += 4) load_rows(u_base, 0, i0);
+            cp_async_arrive_noinc(ufull);
+        }
+        uint32_t phase_bit = 0;                                          // of this group's ring slot
+        int k = 0, cb = 0;
+        for (int ph = 0; ph < n_phases; ++ph) {
+            const bool has_next = ph + 1 < n_phases;
+            const bool next_new_tile = cb == CB - 1;
+            const int ncb = next_new_tile ? 0 : cb + 1;
+            if (has_next && next_new_tile) fetch_rows(k + 1);            // (consumed two stages later)
+            wait_bar(ufull + 8 * (ph & 1), (ph >> 1) & 1);
+            const uint32_t ub = u_base + (ph & 1) * kUBuf + src_off;
+            const uint32_t ubn = u_base + ((ph + 1) & 1) * kUBuf;
+            const uint32_t ibs = idx_base + (k & 1) * kIdxBuf + idx_off;
+#pragma unroll
+            for (int s2 = 0; s2 < NP / 2; ++s2) {
+                // this group's stage: s = 2 * s2 + grp (taps 2s, 2s + 1); s is uniform per warp, the tap tests fold for F = 16
+                const int s = 2 * s2 + grp;
+                const bool second = 2 * s + 1 < F;                        // the stage's second tap exists (F = 15: not in the last stage)
+                const bool tr = p.trace != nullptr && blockIdx.x == 0 && gt == 0 && ph * NP + s < 256;
+                long long* trp = p.trace + (ph * NP + s) * 8;
+                if (tr) trp[0] = clock64();
+                uint32_t slot[8];
+                uint4 v[8];
+                if (!(p.dbg & 1)) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (i < 4 || second) slot[i] = lds_u16(ibs + (2 * s + (i >> 2)) * (TM * 2) + (i & 3) * 64);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (i < 4 || second) v[i] = lds128(ub + slot[i] * kURow);
+                }
+                if (lane == 0) wait_bar(empty_g, phase_bit ^ 1);
+                __syncwarp();
+                if (tr) trp[1] = clock64();
+                if (!(p.dbg & 1)) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (i < 4 || second) sts128(abd + (i >> 2) * kATap + (i & 3) * 512, v[i].x, v[i].y, v[i].z, v[i].w);
+                }
+                if (tr) trp[2] = clock64();
+                // the next phase's rows: issued during this group's first two stages, so they have the rest of the phase to land
+                if (has_next && s2 < 2) {
+                    if (s2 == 0 && next_new_tile) load_idx_block(k + 1);
+                    load_rows(ubn, ncb, 4 * s2);
+                    if (s2 == 1) cp_async_arrive_noinc(ufull + 8 * ((ph + 1) & 1));
+                }
+                if (tr) trp[3] = clock64();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_a(full_g);
+                if (tr) trp[4] = clock64();
+                phase_bit ^= 1;
+            }
+            // every copy thread has finished reading this phase's U buffer (and, at the end of a tile, its index block)
+            asm volatile("bar.sync 1, %0;" ::"n"(kC5CopyThreads) : "memory");
+            if (++cb == CB) { cb = 0; ++k; }
+        }
+    } else if (warp == kC5WWarp) {
+        // ------------------------------------------------------------------ weight stream
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase_bit = 0;
+            for (int k = 0; k < n_my; ++k)
+                for (int cb = 0; cb < CB; ++cb) {
+                    const uint8_t* src = p.w_image + (long long)cb * kTaps * kBTap;
+                    for (int s = 0; s < NP; ++s) {
+                        wait_bar(empty + 8 * stage, phase_bit ^ 1);
+                        if (p.dbg & 4) {
+                            mbar_arrive_a(full + 8 * stage);
+                        } else {
+                            mbar_arrive_expect_tx_a(full + 8 * stage, kBStage);
+                            bulk_load_a(b_base + stage * kBStage, src + (long long)s * kBStage, kBStage, full + 8 * stage);
+                        }
+                        if (++stage == kStages) { stage = 0; phase_bit ^= 1; }
+                    }
+                }
+        }
+    } else if (warp == kC5MmaWarp) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t kIdescMain = instr_desc(0, TM, 128, 0, 0);
+            constexpr uint32_t kIdescLo = instr_desc(0, TM, 64, 0, 0);
+            constexpr uint64_t kDescA = (uint64_t)((kA_LBO >> 4) & 0x3fff) << 16 | (uint64_t)(128 >> 4) << 32 | (uint64_t)1 << 46;
+            constexpr uint64_t kDescB = (uint64_t)((kB_LBO >> 4) & 0x3fff) << 16 | (uint64_t)(128 >> 4) << 32 | (uint64_t)1 << 46;
+            int stage = 0, acc = 0;
+            uint32_t phase_bit = 0, pacc = 0;
+            for (int k = 0; k < n_my; ++k) {
+                wait_bar(acc_empty + 8 * acc, pacc ^ 1);
+                fence_after();
+                const uint32_t d0 = tmem_d + (uint32_t)(acc * acc_cols);
+                int g = 0, g_num = 0, pg = -1;                           // main accumulator of the current K step
+                for (int cb = 0; cb < CB; ++cb)
+#pragma unroll
+                    for (int s = 0; s < NP; ++s) {
+                        const int sidx = (k * CB + cb) * NP + s;
+                        const bool tr = p.trace != nullptr && blockIdx.x == 0 && sidx < 256;
+                        if (tr) p.trace[sidx * 8 + 5] = clock64();
+                        wait_bar(full + 8 * stage, phase_bit);
+                        fence_after();
+                        if (tr) p.trace[sidx * 8 + 6] = clock64();
+                        const uint32_t a16 = (a_base + stage * kAStage) >> 4, b16 = (b_base + stage * kBStage) >> 4;
+#pragma unroll
+                        for (int tap_l = 0; tap_l < 2; ++tap_l) {
+                            if (2 * s + tap_l < F && !(p.dbg & 2)) {
+#pragma unroll
+                                for (int j = 0; j < 2; ++j) {
+                                    const uint32_t ah = a16 + ((tap_l * kATap + j * 2 * kA_LBO) >> 4);
+                                    const uint32_t bb = b16 + ((tap_l * kBTap + j * 2 * kB_LBO) >> 4);
+                                    const uint32_t dg = d0 + (uint32_t)(g * 128);
+                                    umma_f16(dg, kDescA | ah, kDescB | bb, kIdescMain, g == pg);                   // x_hi . [W_hi | W_lo]
+                                    umma_f16(dg + 64, kDescA | (ah + (kAPlane >> 4)), kDescB | bb, kIdescLo, 1);   // x_lo . W_hi
+                                    pg = g;
+                                    g_num += p.n_main;
+                                    if (g_num >= p.steps_total) { g_num -= p.steps_total; ++g; }
+                                }
+                            }
+                        }
+                        umma_commit_a(empty + 8 * stage);
+                        if (tr) p.trace[sidx * 8 + 7] = clock64();
+                        if (++stage == kStages) { stage = 0; phase_bit ^= 1; }
+                    }
+                umma_commit_a(acc_full + 8 * acc);
+                if (++acc == acc_stages) { acc = 0; pacc ^= 1; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (TMEM lane quarter = warp % 4)
+        const int q = warp & 3;
+        float s_in, inv_in, s_w, inv_w;
+        scale_from_amax(__ldg(p.in_amax), s_in, inv_in);
+        scale_from_amax(__ldg(p.w_amax), s_w, inv_w);
+        const float s_ab = s_in * s_w;
+        int acc = 0;
+        uint32_t pacc = 0;
+        float y_max = 0.f;
+        for (int k = 0; k < n_my; ++k) {
+            const int t = t_begin + k;
+            const int row = __ldg(p.tile_rows + (long long)t * TM + q * 32 + lane);
+            if (lane == 0) wait_bar(acc_full + 8 * acc, pacc);
+            __syncwarp();
+            fence_after();
+            const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_cols);
+#pragma unroll 1
+            for (int c0 = 0; c0 < 64; c0 += 16) {
+                if (c0 >= p.c_out) break;
+                float sum[16];
+                uint32_t v[16];
+                tmem_ld16(taddr + 64 + c0, v);                               // cross terms of accumulator 0
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sum[j] = __uint_as_float(v[j]);
+                for (int g = 1; g < p.n_main; ++g) {
+                    tmem_ld16(taddr + g * 128 + 64 + c0, v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sum[j] += __uint_as_float(v[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sum[j] *= kLoInv;
+                for (int g = 0; g < p.n_main; ++g) {
+                    tmem_ld16(taddr + g * 128 + c0, v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sum[j] += __uint_as_float(v[j]);
+                }
+                if (row >= 0 && !(p.dbg & 16)) {
+                    float y[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int o = c0 + j;
+                        const float b = (p.bias != nullptr && o < p.c_out) ? __ldg(p.bias + o) : 0.f;
+                        y[j] = apply_act(fmaf(sum[j], s_ab, b), p.act);
+                        if (o < p.c_out) y_max = fmaxf(y_max, fabsf(y[j]));
+                    }
+                    float* dst = p.out + (long long)row * p.ld_out + c0;
+                    if (c0 + 15 < p.c_out) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4)
+                            *reinterpret_cast<float4*>(dst + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < p.c_out) dst[j] = y[j];
+                    }
+                }
+            }
+            fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(acc_empty + 8 * acc);
+            if (++acc == acc_stages) { acc = 0; pacc ^= 1; }
+        }
+        if (p.out_amax != nullptr) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) y_max = fmaxf(y_max, __shfl_xor_sync(0xffffffffu, y_max, o));
+            if (lane == 0 && y_max > 0.f) atomicMax(p.out_amax, __float_as_uint(y_max));
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == kC5MmaWarp) {
+        fence_after();
+        tmem_dealloc(tmem_d, 512);
+    }
+}
+
+// ======================================================================================== weight gradient
+// dw[f, c, o] += sum_v x[nbr[f, v], c] * dz[v, o]   (autograd of models/bilateralNN.py:219) on the same tile plan.
+//
+// CTA = (32-channel block cb of x, contiguous range of vertex tiles); per tile the distinct x rows are staged once (as in
+// conv5_kernel) and the tile's dz rows are loaded as the B operand.  M = (tap, channel): an M tile is 4 taps x 32
+// channels, so the 16 (padded) taps of one channel block are 4 M tiles x 128 TMEM columns = all of tensor memory: every
+// accumulator stays resident over the CTA's whole vertex range (flushed with fp32 RED every kFlushTiles tiles, which
+// keeps the hi.hi accumulator below ~160 accumulate steps).  K = vertices: both operands are MN-major no-swizzle
+//   element (m, k) at (m / 8) * SBO + (k / 8) * 128 + (k % 8) * 16 + (m % 8) * 2,   SBO = 8 * 128 + 16 (bank spreading)
+// so a staged row chunk (8 channels of one vertex, 16 bytes) is again one LDS.128 / STS.128.
+//   MMA 1: x_hi (M128) . [dz_hi | dz_lo] (N128) -> columns [main | cross];   MMA 2: x_lo . dz_hi (N64) -> cross.
+// Stage = (K half of 64 vertices, M tile): A hi / lo planes of 16.3 KB each, ring of 2; dz halves: ring of 2.
+constexpr uint32_t kW_SBO = 8 * 128 + 16;            // 1040: stride between 8-wide M (or N) groups, K half of 64 vertices
+constexpr int kWPlane = 16 * kW_SBO + 64;            // 16704: one A plane (+64: the lo plane lands 4 bank groups further)
+constexpr int kWAStage = 2 * kWPlane;
+constexpr int kWBHalf = 16 * kW_SBO;                 // 16640: [dz_hi | dz_lo] of 64 vertices
+constexpr int kWSmem = 2 * kUBuf + 2 * kWAStage + 2 * kWBHalf + 2 * kIdxBuf + 2 * TM * 4 + 1024;
+constexpr int kFlushTiles = 16;                      // 16 tiles x 8 K steps = 128 accumulate steps per accumulator
+static_assert(kWSmem <= 232448, "shared memory budget (weight gradient)");
+
+struct Wgrad5Args {
+    const uint8_t* x16;           // h16b image of the layer input (gathered operand)
+    const uint8_t* dz16;          // h16b image of dz (n_rows, c_out)
+    const int* tile_rows;
+    const int* n_uniq;
+    const int* uniq;
+    const unsigned short* local;
+    float* dw;                    // (F, C, Co) fp32, accumulated with RED
+    const uint32_t* x_amax;
+    const uint32_t* dz_amax;
+    int n_tiles, cb_count, cbo_count, filter_size, c_in, c_out, tiles_per_cta;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) wgrad5_kernel(const Wgrad5Args p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 + 2 + 2 + 2 + 2];
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t u_base = smem_base;
+    const uint32_t a_base = u_base + 2 * kUBuf;
+    const uint32_t b_base = a_base + 2 * kWAStage;
+    const uint32_t idx_base = b_base + 2 * kWBHalf;
+    const uint32_t rows_base = idx_base + 2 * kIdxBuf;                           // 2 x 128 output rows (tile_rows)
+    const uint32_t bar0 = smem_u32(bars);
+    const uint32_t full = bar0, empty = full + 16, ufull = empty + 16, bfull = ufull + 16, accb = bfull + 16;   // accb: [0] full, [1] empty
+
+    const int cb = blockIdx.x % p.cb_count;
+    const int range = blockIdx.x / p.cb_count;
+    const int t_begin = range * p.tiles_per_cta;
+    const int t_end = min(p.n_tiles, t_begin + p.tiles_per_cta);
+    const int n_my = max(0, t_end - t_begin);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bars[s], kCopyWarps);
+            mbar_init(&bars[2 + s], 1);
+            mbar_init(&bars[4 + s], kCopyThreads);
+            mbar_init(&bars[6 + s], kCopyThreads);
+        }
+        mbar_init(&bars[8], 1);
+        mbar_init(&bars[9], 4);
+        fence_mbar_init();
+    }
+    if (warp == kMmaWarp) tmem_alloc(&tmem_slot, 512);
+    if (threadIdx.x < 16) {
+        const uint32_t z = u_base + (threadIdx.x >> 3) * kUBuf + kUmax * kURow + (threadIdx.x & 7) * 16;
+        sts128(z, 0, 0, 0, 0);
+    }
+    // the dz buffers: groups a narrow dz (c_out <= 32) never writes must not hold NaN patterns
+    for (int i = threadIdx.x; i < 2 * kWBHalf / 16; i += kThreads) sts128(b_base + i * 16, 0, 0, 0, 0);
+    fence_proxy_async();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_d = tmem_slot;
+
+    if (warp < kCopyWarps) {
+        // ------------------------------------------------------------------ copy warps
+        const int tid = threadIdx.x;
+        const int c8 = tid & 7, rg = tid >> 3;
+        const long long row_bytes = (long long)p.cb_count * kURow;
+        const long long dz_row_bytes = (long long)p.cbo_count * kURow;
+        const uint32_t src_off = c8 * 16;
+        const uint32_t idx_off = rg * 2;
+        // A position of (row = q * 32 + rg within the K half, chunk c8) for tap tl: + tl * 4 * kW_SBO + q * 512
+        const uint32_t dst_off = (c8 >> 2) * kWPlane + (c8 & 3) * kW_SBO + (rg >> 3) * 128 + (rg & 7) * 16;
+        const uint8_t* in_thread = p.x16 + cb * kURow + src_off;
+
+        int urow[kUIters];
+        auto fetch_rows = [&](int k) {
+            const int t = t_begin + k;
+            const int n = __ldg(p.n_uniq + t);
+            const int* up = p.uniq + (long long)t * kUmax + (tid >> 3);
+#pragma unroll
+            for (int i = 0; i < kUIters; ++i) urow[i] = (tid >> 3) + i * (kCopyThreads / 8) < n ? __ldg(up + i * (kCopyThreads / 8)) : -1;
+        };
+        auto load_idx_block = [&](int k) {                               // slots + the tile's output rows
+            cp_async16(idx_base + (k & 1) * kIdxBuf + tid * 16,
+                       reinterpret_cast<const uint8_t*>(p.local) + ((long long)(t_begin + k) * (kTaps * TM)) * 2 + tid * 16);
+            if (tid < TM / 4)
+                cp_async16(rows_base + (k & 1) * (TM * 4) + tid * 16,
+                           reinterpret_cast<const uint8_t*>(p.tile_rows) + ((long long)(t_begin + k) * TM) * 4 + tid * 16);
+        };
+        auto load_rows = [&](uint32_t ub, int i0) {
+            const uint32_t dst = ub + (tid >> 3) * kURow + src_off;
+#pragma unroll
+            for (int i = i0; i < i0 + 4; ++i)
+                if (i < kUIters && urow[i] >= 0) cp_async16(dst + i * (kCopyThreads / 8) * kURow, in_thread + (long long)urow[i] * row_bytes);
+        };
+        // dz rows of K half `h` (0 / 1) of tile k into B buffer `bb`: thread = (chunk j of a 64-byte plane segment, row pair
+        // kk / kk + 4): the 8 lanes of a quarter warp hit 8 different bank groups.  (The tile's row block must have landed.)
+        auto load_dz_half = [&](int k, int h, uint32_t bb) {
+            const int j = tid & 3, r4 = (tid >> 2) & 1;
+            const int shift = p.cbo_count == 2 ? 2 : 1;                           // (plane, block) pairs per row = 2 * cbo = 1 << shift
+            const int n_items = 32 << shift;                                      // (k8, kk < 4) x pairs
+            const uint32_t rb = rows_base + (k & 1) * (TM * 4) + h * 64 * 4;
+            for (int e = tid >> 3; e < n_items; e += kCopyThreads / 8) {
+                const int pair = e & ((1 << shift) - 1), g = e >> shift;          // g = k8 * 4 + kk
+                const int plane = pair & 1, b = pair >> 1;
+                const int row = (g >> 2) * 8 + (g & 3) + 4 * r4;                  // within the half
+                int v;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(rb + row * 4) : "memory");
+                const int n8 = plane * 8 + b * 4 + j;
+                const uint32_t dst = bb + n8 * kW_SBO + (row >> 3) * 128 + (row & 7) * 16;
+                if (v >= 0) cp_async16(dst, p.dz16 + (long long)v * dz_row_bytes + b * kURow + plane * 64 + j * 16);
+                else sts128(dst, 0, 0, 0, 0);
+            }
+        };
+
+        if (n_my > 0) {
+            fetch_rows(0);
+            load_idx_block(0);
+#pragma unroll
+            for (int i0 = 0; i0 < kUIters; i0 += 4) load_rows(u_base, i0);
+            cp_async_arrive_noinc(ufull);
+            wait_bar(ufull, 0);                                                  // (the row block; waiting twice on a phase is fine)
+            load_dz_half(0, 0, b_base);
+            cp_async_arrive_noinc(bfull);
+            load_dz_half(0, 1, b_base + kWBHalf);
+            cp_async_arrive_noinc(bfull + 8);
+        }
+        int stage = 0;
+        uint32_t phase_bit = 0;
+        for (int k = 0; k < n_my; ++k) {
+            const bool has_next = k + 1 < n_my;
+            if (has_next) fetch_rows(k + 1);
+            wait_bar(ufull + 8 * (k & 1), (k >> 1) & 1);
+            const uint32_t ub = u_base + (k & 1) * kUBuf + src_off;
+            const uint32_t ubn = u_base + ((k + 1) & 1) * kUBuf;
+            const uint32_t ibs = idx_base + (k & 1) * kIdxBuf + idx_off;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) {
+                    const int s = h * 4 + mt;                                     // stage number inside the tile
+                    const uint32_t abd = a_base + stage * kWAStage + dst_off;
+                    uint32_t slot[8];
+                    uint4 v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) slot[i] = lds_u16(ibs + ((4 * mt + (i >> 1)) * TM + h * 64 + (i & 1) * 32) * 2);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = lds128(ub + slot[i] * kURow);
+                    // MMAs of stage s - 2 are complete once the stage buffer is free.  s == 1: the previous tile's last stage
+                    // (h = 1, mt = 3) is done -> the dz half-1 buffer may be refilled; s == 5: half 0 of this tile is done.
+                    if (lane == 0) wait_bar(empty + 8 * stage, phase_bit ^ 1);
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) sts128(abd + (i >> 1) * (4 * kW_SBO) + (i & 1) * 512, v[i].x, v[i].y, v[i].z, v[i].w);
+                    if (has_next) {
+                        if (s < 4) {                                              // next tile's x rows
+                            if (s == 0) load_idx_block(k + 1);
+                            load_rows(ubn, 4 * s);
+                            if (s == 3) cp_async_arrive_noinc(ufull + 8 * ((k + 1) & 1));
+                        }
+                        if (s == 5) {                                             // stage 3 (last user of dz half 0) has completed
+                            wait_bar(ufull + 8 * ((k + 1) & 1), ((k + 1) >> 1) & 1);  // next tile's row block (issued at stage 0)
+                            load_dz_half(k + 1, 0, b_base);
+                            cp_async_arrive_noinc(bfull);
+                        }
+                    }
+                    if (s == 1 && k > 0) {                                        // previous tile's stage 7 (last user of half 1) has completed
+                        load_dz_half(k, 1, b_base + kWBHalf);
+                        cp_async_arrive_noinc(bfull + 8);
+                    }
+                    if (mt == 0) wait_bar(bfull + 8 * h, k & 1);                  // this half's dz rows have landed
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_a(full + 8 * stage);
+                    if (++stage == 2) { stage = 0; phase_bit ^= 1; }
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kCopyThreads) : "memory");
+        }
+    } else if (warp == kMmaWarp) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t kIdescMain = instr_desc(0, TM, 128, 1, 1);
+            constexpr uint32_t kIdescLo = instr_desc(0, TM, 64, 1, 1);
+            constexpr uint64_t kDesc = (uint64_t)(128 >> 4) << 16 | (uint64_t)((kW_SBO >> 4) & 0x3fff) << 32 | (uint64_t)1 << 46;
+            int stage = 0, since_flush = 0;
+            uint32_t phase_bit = 0, pacc = 0;
+            for (int k = 0; k < n_my; ++k) {
+                if (since_flush == 0 && k > 0) {                                  // accumulators were flushed: wait until they are drained
+                    wait_bar(accb + 8, pacc);
+                    pacc ^= 1;
+                    fence_after();
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t b16 = (b_base + h * kWBHalf) >> 4;
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt) {
+                        wait_bar(full + 8 * stage, phase_bit);
+                        fence_after();
+                        const uint32_t a16 = (a_base + stage * kWAStage) >> 4;
+                        const uint32_t d = tmem_d + (uint32_t)(mt * 128);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t acc = (since_flush | h | j) != 0;
+                            umma_f16(d, kDesc | (a16 + j * 16), kDesc | (b16 + j * 16), kIdescMain, acc);
+                            umma_f16(d + 64, kDesc | (a16 + (kWPlane >> 4) + j * 16), kDesc | (b16 + j * 16), kIdescLo, 1);
+                        }
+                        umma_commit_a(empty + 8 * stage);
+                        if (++stage == 2) { stage = 0; phase_bit ^= 1; }
+                    }
+                }
+                if (++since_flush == kFlushTiles || k == n_my - 1) {
+                    umma_commit_a(accb);
+                    since_flush = 0;
+                }
+            }
+        }
+    } else if (warp >= 10) {
+        // ------------------------------------------------------------------ flush: TMEM -> RED into dw
+        const int q = warp & 3;
+        float s_x, inv_x, s_z, inv_z;
+        scale_from_amax(__ldg(p.x_amax), s_x, inv_x);
+        scale_from_amax(__ldg(p.dz_amax), s_z, inv_z);
+        const float s_ab = s_x * s_z;
+        const int n_flush = (n_my + kFlushTiles - 1) / kFlushTiles;
+        const int m = q * 32 + lane;                                              // M row of the tile: tap_l * 32 + channel
+        const int ch = cb * 32 + (m & 31);
+        for (int fl = 0; fl < n_flush; ++fl) {
+            if (lane == 0) wait_bar(accb, fl & 1);
+            __syncwarp();
+            fence_after();
+#pragma unroll 1
+            for (int mt = 0; mt < 4; ++mt) {
+                const int f = 4 * mt + (m >> 5);
+                const bool live = f < p.filter_size && ch < p.c_in;
+                const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 128);
+#pragma unroll 1
+                for (int c0 = 0; c0 < 64; c0 += 16) {
+                    if (c0 >= p.c_out) break;
+                    uint32_t vm[16], vc[16];
+                    tmem_ld16(taddr + c0, vm);
+                    tmem_ld16(taddr + 64 + c0, vc);
+                    if (live) {
+                        float* dst = p.dw + ((long long)f * p.c_in + ch) * p.c_out + c0;
+                        float y[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) y[j] = fmaf(__uint_as_float(vc[j]), kLoInv, __uint_as_float(vm[j])) * s_ab;
+                        if (c0 + 15 < p.c_out && (p.c_out & 3) == 0) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) red_add_f32x4(dst + j, make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (c0 + j < p.c_out) atomicAdd(dst + j, y[j]);
+                        }
+                    }
+                }
+            }
+            fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(accb + 8);
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        fence_after();
+        tmem_dealloc(tmem_d, 512);
+    }
+}
+
+void set_attrs() {
+    static bool done = false;
+    if (done) return;
+    cudaFuncSetAttribute(conv5_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(conv5_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(wgrad5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmem);
+    done = true;
+}
+
+int cb_of(int64_t c) { return (int)((c + 31) / 32); }
+
+}  // namespace
+
+extern "C" {
+
+int64_t hpl_h16b_bytes(int64_t n_rows, int64_t channels) { return n_rows * cb_of(channels) * kURow; }
+
+int hpl_h16b_split(const float* x, int64_t ld, int64_t n_rows, int64_t channels, const float* norm, const uint32_t* amax,
+                   void* x16, void* stream) {
+    HPL_CHECK_ARG((x || n_rows == 0) && amax && x16 && channels > 0 && ld >= channels && ld % 4 == 0);
+    HPL_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)x16 & 15) == 0);
+    if (n_rows == 0) return 0;
+    const int cb = cb_of(channels);
+    const long long work = n_rows * cb * 4;
+    h16b_split_kernel<<<(unsigned)((work + 255) / 256), 256, 0, as_stream(stream)>>>(x, ld, n_rows, (int)channels, cb, norm, amax,
+                                                                                  reinterpret_cast<uint4*>(x16));
+    HPL_RETURN_LAST();
+}
+
+int64_t hpl_conv5_workspace(int64_t c_in) { return (int64_t)cb_of(c_in) * kTaps * kBTap + 16; }
+int hpl_conv5_supported(int64_t filter_size, int64_t c_in, int64_t c_out) {
+    const int64_t steps = filter_size * cb_of(c_in) * 2;
+    return filter_size >= 1 && filter_size <= kTaps && c_out >= 1 && c_out <= 64 && c_in >= 1 && steps <= 4 * 160;
+}
+
+/* out[row, :] = act(bias + sum_f x[nbr[f, row]] . w[f]) for every row of the plan's table; x16 = h16b image of x.
+ * w: element (f, c, o) at w + f * w_sf + c * w_sc + o * w_so.  tap_map (device, F ints) or NULL.
+ * workspace: hpl_conv5_workspace(c_in) bytes, 128-byte aligned; workspace_valid != 0: its weight image is current. */
+int hpl_conv5(const void* x16, const void* plan, int64_t n_out_rows, int64_t filter_size, int64_t c_in, int64_t c_out,
+              const float* w, int64_t w_sf, int64_t w_sc, int64_t w_so, const int32_t* tap_map, const float* bias, int act,
+              float* out, int64_t ld_out, void* workspace, int workspace_valid, const uint32_t* in_amax, uint32_t* out_amax,
+              void* stream) {
+    HPL_CHECK_ARG(x16 && plan && w && out && workspace && in_amax);
+    HPL_CHECK_ARG(hpl_conv5_supported(filter_size, c_in, c_out));
+    HPL_CHECK_ARG(((uintptr_t)x16 & 15) == 0 && ((uintptr_t)workspace & 127) == 0 && ((uintptr_t)plan & 255) == 0);
+    HPL_CHECK_ARG(ld_out >= c_out && ld_out % 4 == 0 && ((uintptr_t)out & 15) == 0);
+    if (n_out_rows == 0) return 0;
+    cudaStream_t s = as_stream(stream);
+    set_attrs();
+    const int cb = cb_of(c_in);
+    uint8_t* image = reinterpret_cast<uint8_t*>(workspace);
+    uint32_t* w_amax = reinterpret_cast<uint32_t*>(image + (long long)cb * kTaps * kBTap);
+    if (!workspace_valid) {
+        // max|w| over the (possibly strided) weight: the buffer behind a dense permutation holds exactly the F*C*Co values
+        const int rc = hpl_absmax(w, filter_size * c_in * c_out, w_amax, stream);
+        if (rc != 0) return rc;
+        const long long total = (long long)cb * kTaps * 64 * 4;
+        weight_image5_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w, w_sf, w_sc, w_so, (int)filter_size, (int)c_in, (int)c_out,
+                                                                           cb, tap_map, w_amax, image);
+    }
+    const uint8_t* pb = reinterpret_cast<const uint8_t*>(plan);
+    Conv5Args a;
+    a.in16 = reinterpret_cast<const uint8_t*>(x16);
+    a.w_image = image;
+    a.tile_rows = reinterpret_cast<const int*>(pb + hpl_plan_offset(n_out_rows, 0));
+    a.n_uniq = reinterpret_cast<const int*>(pb + hpl_plan_offset(n_out_rows, 1));
+    a.uniq = reinterpret_cast<const int*>(pb + hpl_plan_offset(n_out_rows, 2));
+    a.local = reinterpret_cast<const unsigned short*>(pb + hpl_plan_offset(n_out_rows, 3));
+    a.bias = bias; a.out = out; a.in_amax = in_amax; a.w_amax = w_amax; a.out_amax = out_amax;
+    a.ld_out = ld_out;
+    a.n_tiles = (int)hpl_plan_tiles(n_out_rows);
+    a.cb_count = cb; a.filter_size = (int)filter_size; a.c_out = (int)c_out; a.act = act;
+    a.steps_total = (int)((filter_size == 15 ? 15 : 16) * cb * 2);
+    a.n_main = (a.steps_total + 159) / 160;
+    { const char* e = getenv("HPL_CONV5_DBG"); a.dbg = e ? atoi(e) : 0; }
+    a.trace = nullptr;
+    { const char* e = getenv("HPL_CONV5_TRACE"); if (e) a.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0)); }
+    const unsigned grid = (unsigned)(a.n_tiles < num_sms() ? a.n_tiles : num_sms());
+    if (filter_size == 15) conv5_kernel<15><<<grid, kC5Threads, kSmem, s>>>(a);
+    else conv5_kernel<16><<<grid, kC5Threads, kSmem, s>>>(a);
+    HPL_RETURN_LAST();
+}
+
+/* dw[f, c, o] += sum_v x[nbr[f, v], c] * dz[v, o] over the plan's table (dw (F, C, Co) fp32, zeroed by the caller).
+ * x16 / dz16: h16b images of x (n_in_rows, c_in) and dz (n_out_rows, c_out); c_out <= 64. */
+int hpl_wgrad5(const void* x16, const void* dz16, const void* plan, int64_t n_out_rows, int64_t filter_size, int64_t c_in,
+               int64_t c_out, float* dw, const uint32_t* x_amax, const uint32_t* dz_amax, void* stream) {
+    HPL_CHECK_ARG(x16 && dz16 && plan && dw && x_amax && dz_amax);
+    HPL_CHECK_ARG(filter_size >= 1 && filter_size <= kTaps && c_in >= 1 && c_out >= 1 && c_out <= 64);
+    HPL_CHECK_ARG(((uintptr_t)x16 & 15) == 0 && ((uintptr_t)dz16 & 15) == 0 && ((uintptr_t)plan & 255) == 0 && ((uintptr_t)dw & 15) == 0);
+    if (n_out_rows == 0) return 0;
+    set_attrs();
+    const uint8_t* pb = reinterpret_cast<const uint8_t*>(plan);
+    Wgrad5Args a;
+    a.x16 = reinterpret_cast<const uint8_t*>(x16);
+    a.dz16 = reinterpret_cast<const uint8_t*>(dz16);
+    a.tile_rows = reinterpret_cast<const int*>(pb + hpl_plan_offset(n_out_rows, 0));
+    a.n_uniq = reinterpret_cast<const int*>(pb + hpl_plan_offset(n_out_rows, 1));
+    a.uniq = reinterpret_cast<const int*>(pb + hpl_plan_offset(n_out_rows, 2));
+    a.local = reinterpret_cast<const unsigned short*>(pb + hpl_plan_offset(n_out_rows, 3));
+    a.dw = dw; a.x_amax = x_amax; a.dz_amax = dz_amax;
+    a.n_tiles = (int)hpl_plan_tiles(n_out_rows);
+    a.cb_count = cb_of(c_in); a.cbo_count = cb_of(c_out);
+    a.filter_size = (int)filter_size; a.c_in = (int)c_in; a.c_out = (int)c_out;
+    int ranges = num_sms() / a.cb_count;
+    if (ranges < 1) ranges = 1;
+    if (ranges > a.n_tiles) ranges = a.n_tiles;
+    a.tiles_per_cta = (a.n_tiles + ranges - 1) / ranges;
+    ranges = (a.n_tiles + a.tiles_per_cta - 1) / a.tiles_per_cta;
+    wgrad5_kernel<<<(unsigned)(ranges * a.cb_count), kThreads, kWSmem, as_stream(stream)>>>(a);
+    HPL_RETURN_LAST();
+}
+
+}  // extern "C"

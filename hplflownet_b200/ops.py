@@ -23,37 +23,74 @@ _tc_workspace = {}
 
 
 # Weight images (pre-split, pre-laid-out fp16 hi/lo copies of a conv weight, built by two small kernels per call) are
-# kept per PARAMETER while its version counter is unchanged: in evaluation the weights never change, in training they
-# change once per optimisation step while every pair of the step reuses them.  Only module parameters are cached (the
-# owner travels as ``w._hpl_owner = (parameter, role)``); ad-hoc weight tensors are always re-imaged.
-WEIGHT_CACHE = True
+# reused across calls only while the caller vouches that parameters do not change: inside ``weight_cache_scope()``
+# (evaluation loops; ``train.train_step`` wraps one optimisation step in it and the images are dropped when the scope
+# ends, i.e. right after the optimizer step), or globally with ``WEIGHT_CACHE = "always"``.  The parameter's version
+# counter and storage pointer are checked as well, but they are not sufficient on their own: ``param.data`` writes
+# (``init.normal_(m.weight.data)`` in the reference's init_weights, EMA swaps, manual clipping) change neither, which
+# is why there is no implicit caching outside a scope.  Only module parameters are cached (the owner travels as
+# ``w._hpl_owner = (parameter, role)``); entries are inserted after the kernels that fill them were enqueued without
+# error, and a weakref finalizer on the parameter removes them when it dies.
+WEIGHT_CACHE = True            # False: never; True: inside weight_cache_scope(); "always": every call
 _weight_images = {}
+_scope_depth = 0
+
+
+class weight_cache_scope:
+    """Within the scope, weight images are reused across calls (the caller promises not to modify parameters inside
+    it); every image is dropped on exit."""
+
+    def __enter__(self):
+        global _scope_depth
+        _scope_depth += 1
+        return self
+
+    def __exit__(self, *a):
+        global _scope_depth
+        _scope_depth -= 1
+        if _scope_depth == 0:
+            _weight_images.clear()
+
+
+def _cache_allowed(param):
+    if not WEIGHT_CACHE:
+        return False
+    if WEIGHT_CACHE == "always" or _scope_depth > 0:
+        return True
+    return False
 
 
 def _cached_workspace(w, nbytes, wide_rows):
-    """(workspace tensor, valid flag) for the weight view w; valid = the image inside is current."""
+    """(workspace tensor, valid flag, commit) for the weight view w; valid = the image inside is current;
+    commit() must be called once the kernels that build the image have been enqueued without error."""
     owner = getattr(w, "_hpl_owner", None)
-    if not WEIGHT_CACHE or owner is None:
-        return _workspace(w.device, nbytes), 0
+    if owner is None or not _cache_allowed(owner[0]):
+        return _workspace(w.device, nbytes), 0, _no_commit
     import weakref
     param, role = owner
     key = (id(param), role, wide_rows, torch.cuda.current_stream(w.device).cuda_stream)
+    sig = (tuple(w.shape), tuple(w.stride()), w.data_ptr())
     ent = _weight_images.get(key)
-    if ent is not None and ent[0]() is param and ent[1] == param._version and ent[2].numel() * 4 >= nbytes \
-            and ent[3] == (tuple(w.shape), tuple(w.stride()), w.data_ptr()):
-        return ent[2], 1
+    if ent is not None and ent[0]() is param and ent[1] == param._version and ent[2].numel() * 4 >= nbytes and ent[3] == sig:
+        return ent[2], 1, _no_commit
+    _weight_images.pop(key, None)
     ws = torch.empty(nbytes // 4 + 4, dtype=torch.float32, device=w.device)
-    if len(_weight_images) > 4096:                      # parameters that died: drop their images
-        for k in [k for k, e in _weight_images.items() if e[0]() is None]:
-            del _weight_images[k]
-    _weight_images[key] = (weakref.ref(param), param._version, ws, (tuple(w.shape), tuple(w.stride()), w.data_ptr()))
-    return ws, 0
+
+    def commit():
+        try:
+            ref = weakref.ref(param, lambda _r, k=key: _weight_images.pop(k, None))
+        except TypeError:
+            return
+        _weight_images[key] = (ref, param._version, ws, sig)
+    return ws, 0, commit
+
+
+def _no_commit():
+    pass
 
 
 def invalidate_weight_cache():
-    """Drop every cached weight image.  The cache follows ``Parameter._version``, which in-place updates through
-    ``param.data`` (old-style optimizers, manual clipping) do NOT bump: call this after such an update.
-    ``train.train_step`` calls it after every optimizer step regardless."""
+    """Drop every cached weight image (after an in-place update the version counter does not see)."""
     _weight_images.clear()
 
 
@@ -277,12 +314,13 @@ def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_majo
             x_amax = absmax(x)
         if not _dense_permutation(w):
             w = w.contiguous()
-        ws, ws_valid = _cached_workspace(w, _lib.load().hpl_blur_gemm_f16_workspace(f, c, co), n_out_rows >= 8192)
+        ws, ws_valid, commit = _cached_workspace(w, _lib.load().hpl_blur_gemm_f16_workspace(f, c, co), n_out_rows >= 8192)
         with _timed(tag):
             _lib.call("hpl_blur_gemm_f16_amax", x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, f, n_out_rows, c, co,
                       w.data_ptr(), w.stride(0), w.stride(1), w.stride(2),
                       bias_ptr, act, out.data_ptr(), out.stride(0), int(out_channel_major),
                       ws.data_ptr(), ws_valid, x_amax.data_ptr(), out_amax.data_ptr() if out_amax is not None else None, _stream())
+        commit()
         out_amax = None
     elif precision == 1:
         ws = _workspace(x.device, _lib.load().hpl_blur_gemm_tc_workspace(f, c, co))
@@ -405,3 +443,68 @@ def channel_sums(x):
     s = torch.zeros(c, dtype=torch.float32, device=x.device)
     _lib.call("hpl_channel_sums", x.data_ptr(), c, n, s.data_ptr(), _stream())
     return s
+
+
+# ------------------------------------------------------------------------------------------ engine 5 (tile plans)
+def h16b_split(x, channels, amax, norm=None):
+    """h16b image (per row and 32-channel block: 32 fp16 hi | 32 fp16 lo) of a vertex-major matrix; norm (rows,):
+    the rows are first multiplied by 1/(norm + 1e-5) (density normalisation fused into the split)."""
+    _f32(x, "x")
+    n = x.size(0)
+    buf = torch.empty(max(_lib.load().hpl_h16b_bytes(n, channels), 16), dtype=torch.uint8, device=x.device)
+    _lib.call("hpl_h16b_split", x.data_ptr(), x.stride(0), n, channels, norm.data_ptr() if norm is not None else None,
+              amax.data_ptr(), buf.data_ptr(), _stream())
+    return buf
+
+
+def conv5_supported(filter_size, c_in, c_out):
+    return bool(_lib.load().hpl_conv5_supported(filter_size, c_in, c_out))
+
+
+_tap_maps = {}
+
+
+def _mirror_map(filter_size, device):
+    key = (filter_size, device)
+    t = _tap_maps.get(key)
+    if t is None:
+        from . import plans
+        m = plans.mirror_taps(filter_size)
+        t = torch.tensor(m, dtype=torch.int32, device=device) if m is not None else False
+        _tap_maps[key] = t
+    return t
+
+
+def conv5(x16, plan, c_in, w, bias, act, x_amax, out=None, out_amax=None, mirror=False, tag="fwd"):
+    """Engine 5 (csrc/gemm_plan.cu): out[v] = act(bias + sum_f x[nbr[f, v]] @ w[f_or_mirror(f)]) over plan's table.
+    x16: h16b image of x; w (F, C, Co) any dense permutation; mirror=True uses w[mirror(f)] (data gradient)."""
+    f, c, co = w.shape
+    assert c == c_in and plan.usable and f == plan.filter_size
+    if out is None:
+        out = alloc_rows(plan.n_rows, co, x16.device)
+    tap_map = None
+    if mirror:
+        tap_map = _mirror_map(f, x16.device)
+        assert tap_map is not False
+    if not _dense_permutation(w):
+        w = w.contiguous()
+    ws, ws_valid, commit = _cached_workspace(w, _lib.load().hpl_conv5_workspace(c) + 256, ("e5", mirror))
+    with _timed(tag):
+        _lib.call("hpl_conv5", x16.data_ptr(), plan.buf.data_ptr(), plan.n_rows, f, c, co,
+                  w.data_ptr(), w.stride(0), w.stride(1), w.stride(2),
+                  tap_map.data_ptr() if tap_map is not None else None,
+                  bias.data_ptr() if bias is not None else None, act, out.data_ptr(), out.stride(0),
+                  ws.data_ptr(), ws_valid, x_amax.data_ptr(), out_amax.data_ptr() if out_amax is not None else None,
+                  _stream())
+    commit()
+    return out
+
+
+def wgrad5(x16, dz16, plan, c_in, c_out, x_amax, dz_amax):
+    """Engine 5 weight gradient: dw (F, C, Co) = sum_v x[nbr[f, v]]^T dz[v] over plan's table (h16b images in)."""
+    assert plan.usable
+    dw = torch.zeros((plan.filter_size, c_in, c_out), dtype=torch.float32, device=x16.device)
+    with _timed("wgrad"):
+        _lib.call("hpl_wgrad5", x16.data_ptr(), dz16.data_ptr(), plan.buf.data_ptr(), plan.n_rows, plan.filter_size,
+                  c_in, c_out, dw.data_ptr(), x_amax.data_ptr(), dz_amax.data_ptr(), _stream())
+    return dw

@@ -1,0 +1,140 @@
+"""Tile plans of a neighbour table (csrc/plan.cu) -- the per-lattice precomputation behind contraction engine 5.
+
+The reference hands the blur step nothing but ``blur_neighbors`` (models/bilateralNN.py:122-125); a plan is derived
+from that tensor alone and cached while the tensor is unchanged (same storage, shape, dtype and version counter), so
+a lattice that serves several layers and the forward / data-gradient / weight-gradient kernels is planned once.
+"""
+import weakref
+
+import numpy as np
+import torch
+
+from . import _lib
+from .transforms import neighbor_offsets
+
+_offsets = {}
+_cache = {}
+RELAX_CHUNK = 48          # relaxation sweeps between convergence checks (one host read each)
+RELAX_MAX = 4096
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _tap_offsets(filter_size, device):
+    """(F, 4) int32 lattice offsets of the taps (transforms.py:112-130) for F = (r+1)^4 - r^4."""
+    key = (filter_size, device)
+    t = _offsets.get(key)
+    if t is None:
+        r = 1
+        while (r + 1) ** 4 - r ** 4 < filter_size:
+            r += 1
+        if (r + 1) ** 4 - r ** 4 != filter_size:
+            return None
+        t = torch.from_numpy(np.ascontiguousarray(neighbor_offsets(r))).to(device)
+        _offsets[key] = t
+    return t
+
+
+def mirror_taps(filter_size):
+    """tap g -> the tap with the opposite offset (the offset set is closed under negation), or None."""
+    r = 1
+    while (r + 1) ** 4 - r ** 4 < filter_size:
+        r += 1
+    if (r + 1) ** 4 - r ** 4 != filter_size:
+        return None
+    offs = neighbor_offsets(r)
+    index = {tuple(o): i for i, o in enumerate(offs.tolist())}
+    return [index[tuple((-o).tolist())] for o in offs]
+
+
+class TilePlan:
+    """Device buffers + host-side facts of one planned table."""
+
+    def __init__(self, buf, n_rows, n_in_rows, filter_size, stats, order, sweeps):
+        self.buf, self.n_rows, self.n_in_rows, self.filter_size = buf, n_rows, n_in_rows, filter_size
+        self.max_uniq, self.overflow, self.sum_uniq = stats
+        self.order, self.sweeps = order, sweeps
+        self.n_tiles = (n_rows + 127) // 128
+        self.symmetric = None          # set by check_symmetric()
+
+    @property
+    def usable(self):
+        return self.overflow == 0
+
+    def view(self, which):
+        """torch view of one plan array (debugging / tests)."""
+        L = _lib.load()
+        lo, hi = L.hpl_plan_offset(self.n_rows, which), L.hpl_plan_offset(self.n_rows, which + 1)
+        raw = self.buf[lo:hi]
+        umax = L.hpl_plan_umax()
+        if which == 0:
+            return raw[:self.n_tiles * 512].view(torch.int32).view(self.n_tiles, 128)
+        if which == 1:
+            return raw[:self.n_tiles * 4].view(torch.int32)
+        if which == 2:
+            return raw[:self.n_tiles * umax * 4].view(torch.int32).view(self.n_tiles, umax)
+        return raw[:self.n_tiles * 4096].view(torch.int16).view(self.n_tiles, 16, 128)
+
+
+def spatial_order(nbr2, n_in_rows=None):
+    """int32 permutation of the table's columns along a Morton curve of reconstructed lattice coordinates, and the
+    number of relaxation sweeps used.  nbr2: (F, H) int32 / int64 CUDA tensor."""
+    f, h = nbr2.shape
+    offs = _tap_offsets(f, nbr2.device)
+    if offs is None or h == 0:
+        return None, 0
+    L = _lib.load()
+    ws = torch.empty(L.hpl_plan_order_workspace(h), dtype=torch.uint8, device=nbr2.device)
+    order = torch.empty(h, dtype=torch.int32, device=nbr2.device)
+    changed = torch.ones(1, dtype=torch.int32, device=nbr2.device)
+    i64 = int(nbr2.dtype == torch.int64)
+    # the relaxation restarts from scratch at every call: run it with a growing sweep count until the last sweep
+    # changes nothing (one host read per attempt; plans are built once per lattice)
+    sweeps = RELAX_CHUNK
+    while True:
+        _lib.call("hpl_plan_order", nbr2.data_ptr(), i64, f, h, offs.data_ptr(), sweeps, ws.data_ptr(),
+                  order.data_ptr(), changed.data_ptr(), _stream())
+        if int(changed.item()) == 0 or sweeps >= RELAX_MAX:
+            break
+        sweeps *= 2
+    return order, sweeps
+
+
+def build(nbr2, n_in_rows=None, order="spatial"):
+    """Plan of the table nbr2 (F, n_rows) whose entries index rows [0, n_in_rows) (default n_rows: a same-lattice table)."""
+    if not (nbr2.is_cuda and nbr2.dtype in (torch.int64, torch.int32) and nbr2.is_contiguous() and nbr2.dim() == 2):
+        raise ValueError("nbr2 must be a contiguous CUDA (F, H) int64/int32 tensor")
+    f, h = nbr2.shape
+    n_in = h if n_in_rows is None else int(n_in_rows)
+    L = _lib.load()
+    sweeps = 0
+    if isinstance(order, str):
+        order, sweeps = spatial_order(nbr2) if order == "spatial" else (None, 0)
+    buf = torch.empty(max(L.hpl_plan_bytes(h), 256), dtype=torch.uint8, device=nbr2.device)
+    stats = torch.zeros(4, dtype=torch.int32, device=nbr2.device)
+    _lib.call("hpl_plan_build", nbr2.data_ptr(), int(nbr2.dtype == torch.int64), f, h, n_in,
+              order.data_ptr() if order is not None else None, buf.data_ptr(), stats.data_ptr(), _stream())
+    s = stats.tolist()
+    return TilePlan(buf, h, n_in, f, (s[0], s[1], s[2]), order, sweeps)
+
+
+def plan_for(nbr2):
+    """Cached plan of a same-lattice table (keyed by the tensor's storage / shape / dtype / version)."""
+    key = (nbr2.data_ptr(), tuple(nbr2.shape), nbr2.dtype, nbr2.device)
+    ent = _cache.get(key)
+    if ent is not None and ent[0]() is not None and ent[1] == nbr2._version:
+        return ent[2]
+    plan = build(nbr2)
+    base = nbr2._base if nbr2._base is not None else nbr2
+    try:
+        ref = weakref.ref(base, lambda _r, k=key: _cache.pop(k, None))
+    except TypeError:
+        return plan
+    _cache[key] = (ref, nbr2._version, plan)
+    return plan
+
+
+def clear():
+    _cache.clear()

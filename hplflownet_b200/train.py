@@ -16,24 +16,32 @@ def epe3d_loss(pred, target):
 
 def allreduce_mean_grads_(params, world_size=None):
     """Average ``p.grad`` over all ranks with a single flat all-reduce (in place).  Works with NCCL (GPU) and
-    gloo (CPU tensors, used by the tests).  Parameters without a gradient contribute zeros."""
+    gloo (CPU tensors, used by the tests).  A parameter that has no gradient on ANY rank keeps ``grad = None`` (the
+    optimizer skips it, as in the reference where unused / frozen parameters are never touched); one that has a
+    gradient on some ranks only gets the mean with zeros from the others.  A presence mask travels with the
+    gradients in the same all-reduce."""
     params = [p for p in params if p.requires_grad]
     if not params:
         return 0
     if world_size is None:
         world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-    for p in params:
-        if p.grad is None:
-            p.grad = torch.zeros_like(p)
     if world_size == 1:
-        return sum(p.numel() for p in params)
-    flat = torch.cat([p.grad.reshape(-1) for p in params])
+        return sum(p.numel() for p in params if p.grad is not None)
+    like = next((p.grad for p in params if p.grad is not None), params[0])
+    present = torch.tensor([0.0 if p.grad is None else 1.0 for p in params], dtype=like.dtype, device=like.device)
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params] + [present])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    seen = flat[-len(params):].tolist()
     flat.div_(world_size)
     off = 0
-    for p in params:
+    for p, cnt in zip(params, seen):
         n = p.numel()
-        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        if cnt > 0:
+            if p.grad is None:
+                p.grad = torch.empty_like(p)
+            p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        else:
+            p.grad = None
         off += n
     return off
 
@@ -41,16 +49,16 @@ def allreduce_mean_grads_(params, world_size=None):
 def train_step(model, optimizer, generator, pairs, collate):
     """One optimisation step over this rank's ``pairs`` = [(pc1 (N,3), pc2 (N,3), flow (N,3)), ...] numpy/torch.
     Returns the mean loss of the local pairs (float tensor on the device, not synchronised)."""
+    from . import ops
     optimizer.zero_grad(set_to_none=True)
     total = None
-    for pc1, pc2, flow in pairs:
-        p1, p2, sf, gd = generator([pc1, pc2, flow])
-        out = model(p1[None], p2[None], collate(gd))
-        loss = epe3d_loss(out, sf[None]) / len(pairs)
-        loss.backward()
-        total = loss.detach() if total is None else total + loss.detach()
+    with ops.weight_cache_scope():           # the weights are constant until optimizer.step(): one image per step
+        for pc1, pc2, flow in pairs:
+            p1, p2, sf, gd = generator([pc1, pc2, flow])
+            out = model(p1[None], p2[None], collate(gd))
+            loss = epe3d_loss(out, sf[None]) / len(pairs)
+            loss.backward()
+            total = loss.detach() if total is None else total + loss.detach()
     allreduce_mean_grads_(list(model.parameters()))
     optimizer.step()
-    from . import ops
-    ops.invalidate_weight_cache()            # the step changed every weight (belt and braces next to the version check)
     return total

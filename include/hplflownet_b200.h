@@ -196,6 +196,51 @@ int hpl_blur_gemm_tma(const void* in16, int64_t n_in_rows, const void* nbr, int 
                       const float* w, const float* bias, int act, float* out, int64_t ld_out,
                       int out_channel_major, void* workspace, const uint32_t* in_amax, void* stream);
 
+/* ---- Tile plans + engine 5 (csrc/plan.cu, csrc/gemm_plan.cu): the same contraction as hpl_blur_gemm_f16
+ * (models/bilateralNN.py:198-221), but every DISTINCT neighbour row of a 128-vertex tile is loaded once.
+ *
+ * A plan is a per-table precomputation (one allocation of hpl_plan_bytes(n_rows) bytes, 256-byte aligned; array
+ * `which` = 0 tile_rows (n_tiles,128) i32, 1 n_uniq (n_tiles) i32, 2 uniq (n_tiles, umax) i32, 3 local
+ * (n_tiles,16,128) u16 starts at hpl_plan_offset(n_rows, which)).  Tiles are runs of 128 entries of `order` (a
+ * permutation of the table's columns, NULL = identity); hpl_plan_order derives a spatially coherent order from the
+ * table alone by propagating lattice coordinates (coord(nbr[f,v]) = coord(v) + offsets[f], offsets (F,4) int32 =
+ * transforms.py:112-130) and sorting along a Morton curve.  stats (4 x int32, device): [0] max distinct rows of a
+ * tile, [1] tiles above hpl_plan_umax() (such a plan must not be used: take hpl_blur_gemm_f16), [2] sum of distinct
+ * rows over tiles. */
+int64_t hpl_plan_tiles(int64_t n_rows);
+int64_t hpl_plan_umax(void);
+int64_t hpl_plan_offset(int64_t n_rows, int which);
+int64_t hpl_plan_bytes(int64_t n_rows);
+int hpl_plan_build(const void* nbr, int idx64, int64_t filter_size, int64_t n_rows, int64_t n_in_rows,
+                   const int32_t* order, void* plan, int32_t* stats, void* stream);
+int64_t hpl_plan_order_workspace(int64_t n_rows);
+int hpl_plan_order(const void* nbr, int idx64, int64_t filter_size, int64_t n_rows, const int32_t* offsets,
+                   int iterations, void* workspace, int32_t* order, int32_t* changed_out, void* stream);
+
+/* "h16b" operand image: per row and 32-channel block one 128-byte line [32 fp16 hi | 32 fp16 lo],
+ * x / s = hi + lo * 2^-11, s the power of two derived from *amax (any upper bound of max|x| within 2^10 works).
+ * norm != NULL: x[v,:] is first multiplied by 1/(norm[v] + 1e-5) (bilateralNN.py:185-186 fused into the split). */
+int64_t hpl_h16b_bytes(int64_t n_rows, int64_t channels);
+int hpl_h16b_split(const float* x, int64_t ld, int64_t n_rows, int64_t channels, const float* norm,
+                   const uint32_t* amax, void* x16, void* stream);
+
+/* out[row,:] = act(bias + sum_f x[nbr[f,row]] . w[f]) over the plan's table; x16 = h16b image of x (n_in_rows, c_in).
+ * w element (f,c,o) at w + f*w_sf + c*w_sc + o*w_so; tap_map (device, F int32, may be NULL): kernel tap g uses
+ * w[tap_map[g]] (data gradient: mirrored tap, transposed weight).  workspace: hpl_conv5_workspace(c_in) bytes,
+ * 128-byte aligned; workspace_valid != 0: the weight image inside is current.  Supported: hpl_conv5_supported(). */
+int64_t hpl_conv5_workspace(int64_t c_in);
+int hpl_conv5_supported(int64_t filter_size, int64_t c_in, int64_t c_out);
+int hpl_conv5(const void* x16, const void* plan, int64_t n_out_rows, int64_t filter_size, int64_t c_in,
+              int64_t c_out, const float* w, int64_t w_sf, int64_t w_sc, int64_t w_so, const int32_t* tap_map,
+              const float* bias, int act, float* out, int64_t ld_out, void* workspace, int workspace_valid,
+              const uint32_t* in_amax, uint32_t* out_amax, void* stream);
+
+/* Weight gradient on the same plan (autograd of bilateralNN.py:219):
+ *   dw[f, c, o] += sum_v x[nbr[f, v], c] * dz[v, o],  dw (F, C, Co) fp32 zeroed by the caller; x16 / dz16 = h16b images
+ * of x (n_in_rows, c_in) and dz (n_out_rows, c_out), c_out <= 64. */
+int hpl_wgrad5(const void* x16, const void* dz16, const void* plan, int64_t n_out_rows, int64_t filter_size,
+               int64_t c_in, int64_t c_out, float* dw, const uint32_t* x_amax, const uint32_t* dz_amax, void* stream);
+
 /* sums[c] += sum_v rows[v, c]  (conv bias gradients). rows (n_rows, ld) vertex-major. */
 int hpl_column_sums(const float* rows, int64_t ld, int64_t n_rows, int64_t channels, float* sums,
                     void* stream);

@@ -193,8 +193,9 @@ def test_bcl_tma_engine_matches_default_engine(monkeypatch):
 
 
 def test_weight_image_cache_follows_parameter_updates():
-    """The per-parameter weight-image cache (ops.WEIGHT_CACHE) must be invisible: same results as without it, and an
-    in-place parameter update (what an optimizer step does) must invalidate it."""
+    """The per-parameter weight-image cache (ops.weight_cache_scope) must be invisible: same results as without it, an
+    in-place parameter update (what an optimizer step does) must invalidate it, and outside a scope nothing is cached
+    (param.data writes bump no version counter)."""
     from hplflownet_b200 import ops
     d = _lattice(2048, 9, 1.0)
     torch.manual_seed(1)
@@ -210,17 +211,26 @@ def test_weight_image_cache_follows_parameter_updates():
         y.sum().backward()
         return y.detach().clone(), f.grad.clone()
     try:
-        y0, g0 = run(True)
-        y1, g1 = run(True)                       # second call: images served from the cache
-        assert_close(y1, y0, "cached second call")        # (not bitwise: the splat's RED order varies)
-        assert_close(g1, g0, "cached second call, grad")
-        with torch.no_grad():
-            for p in mod.parameters():
-                p.mul_(1.5)                      # in-place: bumps the version counter
-        y2, g2 = run(True)
-        y3, g3 = run(False)
-        assert not torch.allclose(y2, y0)
-        assert_close(y2, y3, "after update, cached vs uncached")
-        assert_close(g2, g3, "grad after update, cached vs uncached")
+        with ops.weight_cache_scope():
+            y0, g0 = run(True)
+            assert len(ops._weight_images) > 0
+            y1, g1 = run(True)                       # second call: images served from the cache
+            assert_close(y1, y0, "cached second call")        # (not bitwise: the splat's RED order varies)
+            assert_close(g1, g0, "cached second call, grad")
+            with torch.no_grad():
+                for p in mod.parameters():
+                    p.mul_(1.5)                      # in-place: bumps the version counter
+            y2, g2 = run(True)
+            y3, g3 = run(False)
+            assert not torch.allclose(y2, y0)
+            assert_close(y2, y3, "after update, cached vs uncached")
+            assert_close(g2, g3, "grad after update, cached vs uncached")
+        assert len(ops._weight_images) == 0          # dropped with the scope
+        for p in mod.parameters():
+            p.data.mul_(0.5)                         # .data write: invisible to the version counter
+        y4, _ = run(True)                            # outside a scope: never cached
+        y5, _ = run(False)
+        assert len(ops._weight_images) == 0
+        assert_close(y4, y5, "no caching outside a scope")
     finally:
         ops.WEIGHT_CACHE = True

@@ -16,22 +16,15 @@ i64, i32, vp, cint = ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_i
 SIGNATURES = {
     "hpl_version": [],
     "hpl_sm_arch": [],
-    "hpl_scatter_rows": [vp, vp, vp, cint, i64, i64, vp, i64, vp, vp],
+    "hpl_scatter_rows": [vp, vp, vp, cint, i64, i64, vp, i64, i64, vp, vp, vp],
     "hpl_normalize_rows": [vp, i64, i64, i64, vp, vp, vp],
-    "hpl_gather_rows": [vp, i64, vp, vp, cint, vp, vp, i64, i64, vp, vp],
+    "hpl_gather_rows": [vp, i64, vp, vp, cint, vp, vp, i64, i64, i64, vp, vp],
     "hpl_blur_gemm": [vp, i64, i64, vp, cint, i64, i64, i64, i64, vp, vp, cint, vp, i64, cint, cint, vp],
-    "hpl_blur_gemm_tc_workspace": [i64, i64, i64],
-    "hpl_blur_gemm_tc": [vp, i64, i64, vp, cint, i64, i64, i64, i64, vp, vp, cint, vp, i64, cint, vp, vp, vp],
     "hpl_blur_wgrad": [vp, i64, i64, vp, cint, i64, i64, i64, i64, vp, i64, vp, vp, vp],
-    "hpl_blur_wgrad_tc": [vp, i64, i64, vp, cint, i64, i64, i64, i64, vp, i64, vp, vp, vp, vp],
     "hpl_absmax": [vp, i64, vp, vp],
     "hpl_blur_gemm_f16_workspace": [i64, i64, i64],
     "hpl_blur_gemm_f16": [vp, i64, i64, vp, cint, i64, i64, i64, i64, vp, vp, cint, vp, i64, cint, vp, vp, vp],
     "hpl_blur_wgrad_f16": [vp, i64, i64, vp, cint, i64, i64, i64, i64, vp, i64, vp, vp, vp, vp, vp],
-    "hpl_split16_bytes": [i64, i64],
-    "hpl_split16": [vp, i64, i64, i64, vp, vp, vp],
-    "hpl_blur_gemm_p16": [vp, i64, vp, cint, i64, i64, i64, i64, vp, vp, cint, vp, i64, cint, vp, vp, vp],
-    "hpl_blur_wgrad_p16": [vp, i64, vp, cint, i64, i64, i64, i64, vp, vp, vp, vp, vp],
     "hpl_blur_gemm_f16_amax": [vp, i64, i64, vp, cint, i64, i64, i64, i64, vp, i64, i64, i64, vp, cint, vp, i64, cint, vp, cint, vp, vp, vp],
     "hpl_normalize_rows_amax": [vp, i64, i64, i64, vp, vp, vp, vp],
     "hpl_cm_to_rows_amax": [vp, i64, i64, i64, vp, i64, vp, vp],
@@ -46,8 +39,8 @@ SIGNATURES = {
     "hpl_cm_to_rows": [vp, i64, i64, i64, vp, i64, vp],
     "hpl_rows_to_cm": [vp, i64, i64, i64, vp, i64, vp],
     "hpl_channel_sums": [vp, i64, i64, vp, vp],
-    "hpl_corr_gather": [vp, i64, vp, vp, i64, vp, cint, vp, cint, vp, i64, i64, i64, i64, i64, vp],
-    "hpl_corr_scatter": [vp, i64, vp, vp, cint, vp, i64, vp, i64, i64, i64, i64, i64, vp],
+    "hpl_corr_gather": [vp, i64, vp, vp, i64, vp, cint, vp, cint, vp, i64, i64, i64, i64, i64, i64, i64, vp],
+    "hpl_corr_scatter": [vp, i64, vp, vp, cint, vp, i64, vp, i64, i64, i64, i64, i64, i64, i64, vp],
     "hpl_lattice_init_range": [vp, vp],
     "hpl_lattice_points": [vp, i64, ctypes.c_float, vp, vp, vp, vp, vp, vp],
     "hpl_lattice_table_capacity": [i64],
@@ -60,7 +53,7 @@ SIGNATURES = {
     "hpl_plan_umax": [],
     "hpl_plan_offset": [i64, cint],
     "hpl_plan_bytes": [i64],
-    "hpl_plan_build": [vp, cint, i64, i64, i64, vp, vp, vp, vp],
+    "hpl_plan_build": [vp, cint, i64, i64, i64, vp, vp, vp, vp, vp],
     "hpl_plan_order_workspace": [i64],
     "hpl_plan_order": [vp, cint, i64, i64, vp, cint, vp, vp, vp, vp],
     "hpl_h16b_bytes": [i64, i64],
@@ -74,21 +67,20 @@ SIGNATURES = {
 }
 
 
-RETURNS_I64 = {"hpl_lattice_table_capacity", "hpl_lattice_scan_blocks", "hpl_blur_gemm_tc_workspace",
-               "hpl_blur_gemm_f16_workspace", "hpl_split16_bytes", "hpl_h16_bytes", "hpl_blur_gemm_tma_workspace",
+RETURNS_I64 = {"hpl_lattice_table_capacity", "hpl_lattice_scan_blocks",                "hpl_blur_gemm_f16_workspace", "hpl_h16_bytes", "hpl_blur_gemm_tma_workspace",
                "hpl_plan_tiles", "hpl_plan_umax", "hpl_plan_offset", "hpl_plan_bytes", "hpl_plan_order_workspace",
                "hpl_h16b_bytes", "hpl_conv5_workspace", "hpl_conv5_supported"}   # sizes, not status codes
 
 # kernels enqueued per call (for bench.py's gpu_launches claim)
 LAUNCHES = {
-    "hpl_scatter_rows": 1, "hpl_normalize_rows": 2, "hpl_gather_rows": 1, "hpl_blur_gemm": 1, "hpl_blur_gemm_tc": 2,
-    "hpl_blur_wgrad": 2, "hpl_blur_wgrad_tc": 2, "hpl_absmax": 1, "hpl_blur_gemm_f16_amax": 3, "hpl_normalize_rows_amax": 2, "hpl_cm_to_rows_amax": 1, "hpl_act_backward_stats": 1,
-    "hpl_split16": 1, "hpl_h16_split": 1, "hpl_blur_gemm_tma": 3, "hpl_blur_gemm_p16": 3, "hpl_blur_wgrad_p16": 1, "hpl_blur_gemm_f16": 3, "hpl_blur_wgrad_f16": 2, "hpl_act_backward": 1, "hpl_transpose_table": 1, "hpl_cm_to_rows": 1,
+    "hpl_scatter_rows": 1, "hpl_normalize_rows": 2, "hpl_gather_rows": 1, "hpl_blur_gemm": 1, 
+    "hpl_blur_wgrad": 2, "hpl_absmax": 1, "hpl_blur_gemm_f16_amax": 3, "hpl_normalize_rows_amax": 2, "hpl_cm_to_rows_amax": 1, "hpl_act_backward_stats": 1,
+    "hpl_h16_split": 1, "hpl_blur_gemm_tma": 3, "hpl_blur_gemm_f16": 3, "hpl_blur_wgrad_f16": 2, "hpl_act_backward": 1, "hpl_transpose_table": 1, "hpl_cm_to_rows": 1,
     "hpl_rows_to_cm": 1, "hpl_channel_sums": 1, "hpl_fill_zero": 1, "hpl_fill_i32": 1,
     "hpl_corr_gather": 1, "hpl_corr_scatter": 1, "hpl_column_sums": 1,
     "hpl_lattice_init_range": 1, "hpl_lattice_points": 1, "hpl_lattice_insert": 6,
     "hpl_lattice_neighbors": 1, "hpl_lattice_corr_table": 1, "hpl_lattice_next_points": 1,
-    "hpl_plan_build": 1, "hpl_h16b_split": 1, "hpl_conv5": 3, "hpl_wgrad5": 1,
+    "hpl_plan_build": 2, "hpl_h16b_split": 1, "hpl_conv5": 3, "hpl_wgrad5": 1,
 }
 launch_count = 0
 

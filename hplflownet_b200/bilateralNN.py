@@ -21,8 +21,6 @@ from .module_utils import Conv2dReLU
 
 __all__ = ["BilateralConvFlex", "SparseSum", "sparse_sum"]
 
-FUSE_NORMALISATION = False
-
 
 def _act_code(has_act, use_leaky):
     if not has_act:
@@ -78,6 +76,15 @@ def conv_weight_grad(dw, like):
     return dw.permute(2, 1, 0).reshape(tuple(like)).contiguous()
 
 
+def _plan_for_first_layer(nbr2, c_in, c_out0):
+    """Tile plan of the neighbour table when engine 5 can take the stack's first layer, else None."""
+    if not ops.engine5_enabled() or not ops.conv5_supported(nbr2.size(0), c_in, c_out0):
+        return None
+    from . import plans
+    plan = plans.plan_for(nbr2)
+    return plan if plan.usable else None
+
+
 class _BCLFunction(torch.autograd.Function):
     """splat -> conv stack -> slice with a hand-written backward (autograd in the reference)."""
 
@@ -88,31 +95,36 @@ class _BCLFunction(torch.autograd.Function):
         c_in = feat.size(0)
         nbr2 = nbr[0].contiguous()                           # (F, H)
         h = nbr2.size(1)
-        inv, fuse_norm = None, False
-        # engine 2: the producer of the lattice rows records max|rows| itself (no separate absmax pass)
-        lat_amax = ops.amax_slots(feat.device, 1) if (ops.fused_stats() and c_in % 4 == 0) else None
+        layers = [(kernel_weight(params[2 * l]), params[2 * l + 1].detach(), acts[l]) for l in range(len(acts))]
+        plan = _plan_for_first_layer(nbr2, c_in, layers[0][0].size(2))
+        inv, first5, lat = None, None, None
+        # the producer of the lattice rows records max|rows| (or a bound of it) itself: no separate absmax pass
+        lat_amax = ops.amax_slots(feat.device, 1) if (ops.fused_stats() and (c_in % 4 == 0 or plan is not None)) else None
         if do_splat:
             bary_i, off_i = in_bary[0].contiguous(), in_off[0].contiguous()
-            lat, wsum = ops.scatter_rows(feat, bary_i, off_i, h, use_norm)
-            if not use_norm:
-                lat_amax = None
-            if use_norm:
-                # The contraction kernels can also apply 1/(wsum+1e-5) while gathering (row_scale), saving
-                # this pass; measured on B200 the extra dependent load costs the forward GEMM more (+70 us
-                # per 32 clouds) than the 25 us pass it removes, so it is off by default.
-                fuse_norm = FUSE_NORMALISATION and ops.tc_path(c_in)
-                if fuse_norm:
-                    inv, lat_amax = ops.reciprocal_(wsum), None
+            if plan is not None and use_norm:
+                # engine 5: the normalised rows only ever exist as their pre-split image.  |S[v]| <= max|feat| (a convex
+                # combination, bilateralNN.py:150-186), so the splat kernel's fused max|feat| is a valid operand scale.
+                raw, wsum = ops.scatter_rows(feat, bary_i, off_i, h, True, in_amax=lat_amax)
+                x16 = ops.h16b_split(raw, c_in, lat_amax, norm=wsum)
+                inv = ops.reciprocal_(wsum)
+                first5 = _stack.First5(x16, lat_amax, plan)
+            else:
+                lat, wsum = ops.scatter_rows(feat, bary_i, off_i, h, use_norm)
+                if use_norm:
+                    inv = ops.normalize_rows_(lat, c_in, wsum, amax=lat_amax if c_in % 4 == 0 else None)
                 else:
-                    inv = ops.normalize_rows_(lat, c_in, wsum, amax=lat_amax)
+                    lat_amax = None
         else:
             bary_i = off_i = None
             lat = ops.cm_to_rows(feat, amax=lat_amax)
+        if plan is not None and first5 is None:
+            amax = lat_amax if lat_amax is not None else ops.absmax(lat)
+            first5 = _stack.First5(ops.h16b_split(lat, c_in, amax), amax, plan)
+            lat = None
 
-        layers = [(kernel_weight(params[2 * l]), params[2 * l + 1].detach(), acts[l]) for l in range(len(acts))]
-        scale0 = inv if (do_splat and use_norm and fuse_norm) else None
-        xs, chans, out_cm = _stack.forward(lat, c_in, h, layers, nbr2, last_channel_major=not do_slice,
-                                           first_row_scale=scale0, x_amax=lat_amax)
+        xs, chans, out_cm, amaxs = _stack.forward(lat, c_in, h, layers, nbr2, last_channel_major=not do_slice,
+                                                  x_amax=lat_amax, first5=first5)
 
         if do_slice:
             bary_o, off_o = out_bary[0].contiguous(), out_off[0].contiguous()
@@ -123,8 +135,8 @@ class _BCLFunction(torch.autograd.Function):
             out = out_cm if out_cm is not None else ops.rows_to_cm(xs[-1], chans[-1])
 
         ctx.cfg, ctx.chans, ctx.h = cfg, chans, h
-        ctx.xs, ctx.layers, ctx.inv, ctx.scale0 = xs, layers, inv, scale0
-        ctx.amaxs = _stack.forward.last_amaxs
+        ctx.xs, ctx.layers, ctx.inv, ctx.first5 = xs, layers, inv, first5
+        ctx.amaxs = amaxs
         ctx.idx = (bary_i, off_i, nbr2, bary_o, off_o)
         ctx.has_slice_bias = slice_bias is not None
         ctx.param_shapes = [p.shape for p in params]
@@ -147,7 +159,7 @@ class _BCLFunction(torch.autograd.Function):
         need_feat = ctx.needs_input_grad[1]
         need_param = [ctx.needs_input_grad[8 + 2 * l] or ctx.needs_input_grad[9 + 2 * l] for l in range(len(layers))]
         dx, pg = _stack.backward(dx, xs, chans, layers, h, nbr2, lambda: ops.transpose_table(nbr2, h),
-                                 need_feat, need_param, first_row_scale=ctx.scale0, amaxs=ctx.amaxs)
+                                 need_feat, need_param, amaxs=ctx.amaxs, first5=ctx.first5)
         grads = []
         for l, g_l in enumerate(pg):
             if g_l is None:

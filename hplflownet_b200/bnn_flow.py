@@ -37,8 +37,13 @@ class _CorrFunction(torch.autograd.Function):
         f1, f2 = feat1[0].contiguous(), feat2[0].contiguous()          # (C, H1), (C, H2)
         c, h1 = f1.shape
         h2 = f2.size(1)
-        i1c, i2c = i1[0].contiguous(), i2[0].contiguous()              # (P, H1), (F, P, H1)
+        i1c, _ = ops._idx(i1[0].contiguous(), "pc1_corr_indices")       # (P, H1)
+        i2c, _ = ops._idx(i2[0].contiguous(), "pc2_corr_indices")       # (F, P, H1)
+        if i1c.dtype != i2c.dtype:                                      # the kernels read both tables at one width
+            i2c = i2c.to(i1c.dtype)
         patch, filt = i1c.size(0), i2c.size(0)
+        if i1c.size(-1) != h1 or i2c.size(-1) != h1 or i2c.size(1) != patch:
+            raise ValueError("correlation tables do not match feat1: pc1 %s, pc2 %s, H1 %d" % (tuple(i1c.shape), tuple(i2c.shape), h1))
 
         # ---- lattice-1 operand: [splat(prev) | feat1] (bnn_flow.py:119-168); lattice-2: feat2
         rows1 = ops.cm_to_rows(f1)                                      # (H1, ld)
@@ -46,7 +51,10 @@ class _CorrFunction(torch.autograd.Function):
         c_prev = 0
         if prev is not None:
             c_prev = prev.size(1)
-            bary, off = bary1[0].contiguous(), off1[0].contiguous()
+            bary = ops._f32(bary1[0].contiguous(), "barycentric1")
+            off, _ = ops._idx(off1[0].contiguous(), "lattice_offset1")
+            if bary.shape != (4, prev.size(-1)) or off.shape != bary.shape:
+                raise ValueError("barycentric1 / lattice_offset1 must be (1, 4, N) like prev_corr_feat")
             prow, wsum = ops.scatter_rows(prev[0].contiguous(), bary, off, h1, use_norm)
             if use_norm:
                 inv = ops.normalize_rows_(prow, c_prev, wsum)
@@ -71,13 +79,13 @@ class _CorrFunction(torch.autograd.Function):
         z = torch.empty((h1 * filt, wp), dtype=torch.float32, device=dev)
         _lib.call("hpl_corr_gather", t1.data_ptr(), t1.stride(0), i1c.data_ptr(), t2.data_ptr(), t2.stride(0),
                   i2c.data_ptr(), int(i1c.dtype == torch.int64), b0p.data_ptr(), corr_acts[0], z.data_ptr(),
-                  z.stride(0), wp, patch, filt, h1, ops._stream())
+                  z.stride(0), wp, patch, filt, h1, h1, h2, ops._stream())
         del t1, t2
 
         # ---- remaining 1x1x1 corr layers on (H1*F, O) rows
         corr_layers = [(kernel_weight(params[2 * l]), params[2 * l + 1].detach(), corr_acts[l])
                        for l in range(1, n_corr)]
-        zs, zch, _ = _stack.forward(z, o1, h1 * filt, corr_layers)
+        zs, zch, _, z_amaxs = _stack.forward(z, o1, h1 * filt, corr_layers)
         o_last = zch[-1]
         ldz = zs[-1].stride(0)
 
@@ -89,11 +97,12 @@ class _CorrFunction(torch.autograd.Function):
         blur_layers += [(kernel_weight(params[base + 2 * l]), params[base + 2 * l + 1].detach(), blur_acts[l])
                         for l in range(1, n_blur)]
         zf = zs[-1].view(h1, filt * ldz)
-        ys, ych, out_cm = _stack.forward(zf, filt * ldz, h1, blur_layers, last_channel_major=True)
+        ys, ych, out_cm, y_amaxs = _stack.forward(zf, filt * ldz, h1, blur_layers, last_channel_major=True)
         out = out_cm if out_cm is not None else ops.rows_to_cm(ys[-1], ych[-1])
 
         ctx.cfg, ctx.dims = cfg, (c, c_prev, c1, h1, h2, patch, filt, o1, wp, o_last, ldz)
         ctx.saved = (s1, s2, wa, wb, z, zs, zch, corr_layers, ys, ych, blur_layers, inv, bary, off, i1c, i2c)
+        ctx.amaxs = (z_amaxs, y_amaxs)
         ctx.param_shapes = [p.shape for p in params]
         return out.unsqueeze(0)
 
@@ -112,7 +121,7 @@ class _CorrFunction(torch.autograd.Function):
         # ---- displacement filter stack
         dy = ops.cm_to_rows(grad_out[0].contiguous())
         need_p = [need(base + 2 * l) or need(base + 2 * l + 1) for l in range(n_blur)]
-        dzf, pg = _stack.backward(dy, ys, ych, blur_layers, h1, None, None, True, need_p)
+        dzf, pg = _stack.backward(dy, ys, ych, blur_layers, h1, None, None, True, need_p, amaxs=ctx.amaxs[1])
         for l, g in enumerate(pg):
             if g is None:
                 continue
@@ -127,7 +136,7 @@ class _CorrFunction(torch.autograd.Function):
         # ---- 1x1x1 corr layers
         dz = dzf.view(h1 * filt, ldz)
         need_p = [need(2 * l) or need(2 * l + 1) for l in range(1, n_corr)]
-        dz, pg = _stack.backward(dz, zs, zch, corr_layers, h1 * filt, None, None, True, need_p)
+        dz, pg = _stack.backward(dz, zs, zch, corr_layers, h1 * filt, None, None, True, need_p, amaxs=ctx.amaxs[0])
         for k, g in enumerate(pg):
             if g is not None:
                 l = k + 1
@@ -140,7 +149,7 @@ class _CorrFunction(torch.autograd.Function):
         dt2 = torch.zeros((h2, patch * wp), dtype=torch.float32, device=dev)
         _lib.call("hpl_corr_scatter", dz.data_ptr(), dz.stride(0), i1c.data_ptr(), i2c.data_ptr(),
                   int(i1c.dtype == torch.int64), dt1.data_ptr(), dt1.stride(0), dt2.data_ptr(), dt2.stride(0),
-                  wp, patch, filt, h1, ops._stream())
+                  wp, patch, filt, h1, h1, h2, ops._stream())
         if need(0) or need(1):
             dwa, _ = ops.blur_wgrad(s1, c1, None, h1, dt1, patch * wp, 1, want_db=False)     # (1, C1, P*wp)
             dwb, _ = ops.blur_wgrad(s2, c, None, h2, dt2, patch * wp, 1, want_db=False)      # (1, C,  P*wp)

@@ -114,6 +114,25 @@ plan_tiles_kernel(const void* __restrict__ nbr, int filter_size, long long n_row
     }
 }
 
+// ------------------------------------------------------------------------------------------- symmetry check
+// The data gradient of the convolution gathers through the TRANSPOSED table.  For a lattice table the transpose is a
+// row permutation of the table itself: u = nbr[f, v]  <=>  v = nbr[mirror(f), u]  (the offset set is closed under
+// negation, transforms.py:112-130).  Counts the entries that violate this (0 for every table the lattice builder makes;
+// arbitrary user tables fall back to an explicit transpose).
+template <bool I64>
+__global__ void plan_symmetry_kernel(const void* __restrict__ nbr, int filter_size, long long n_rows,
+                                     const int* __restrict__ mirror, int* __restrict__ violations) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)filter_size * n_rows) return;
+    const int f = (int)(t / n_rows);
+    const long long v = t - (long long)f * n_rows;
+    const int u = load_idx<I64>(nbr, t);
+    if (u < 0) return;
+    bool bad = u >= n_rows;
+    if (!bad) bad = load_idx<I64>(nbr, (long long)mirror[f] * n_rows + u) != (int)v;
+    if (bad) atomicAdd(violations, 1);
+}
+
 // --------------------------------------------------------------------------------- coordinate reconstruction
 // state per vertex: root (component label = smallest vertex id reached so far) and integer coordinates relative to
 // that root.  Jacobi relaxation (read buffer `a`, write buffer `b`): a vertex adopts the smallest root among itself
@@ -173,9 +192,8 @@ __device__ __forceinline__ unsigned long long spread3(unsigned v) {     // 21 bi
     return x;
 }
 
-// key = component (root id, high bits) | Morton code of the root-relative coordinates (low 3 * bits_per_axis bits).
-// The three lattice coordinates are first mapped to a roughly isotropic frame (u = x - z, v = y - z, w = x + y + z
-// keeps neighbouring vertices within a few units of each other on every axis).
+// key = component (root id, high bits) | Morton code of the root-relative coordinates (low 3 * bits_per_axis bits)
+// (the first three of the four hyperplane coordinates; tools/plan_probe.py: a Euclidean embedding is no better).
 __global__ void plan_keys_kernel(const VState* __restrict__ a, long long n_rows, const int* __restrict__ mins,
                                  int bits_per_axis, unsigned long long* __restrict__ keys, int* __restrict__ vals) {
     const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -295,7 +313,7 @@ int64_t hpl_plan_offset(int64_t n_rows, int which) {
 int64_t hpl_plan_bytes(int64_t n_rows) { return hpl_plan_offset(n_rows, 4); }
 
 int hpl_plan_build(const void* nbr, int idx64, int64_t filter_size, int64_t n_rows, int64_t n_in_rows, const int32_t* order,
-                   void* plan, int32_t* stats, void* stream) {
+                   const int32_t* tap_mirror, void* plan, int32_t* stats, void* stream) {
     HPL_CHECK_ARG(nbr && plan && stats && filter_size > 0 && filter_size <= kTaps && n_rows >= 0 && n_in_rows >= 0);
     HPL_CHECK_ARG(n_rows < (1LL << 31) - TM && n_in_rows < (1LL << 31) && ((uintptr_t)plan & 255) == 0);
     cudaStream_t s = as_stream(stream);
@@ -312,6 +330,13 @@ int hpl_plan_build(const void* nbr, int idx64, int64_t filter_size, int64_t n_ro
         plan_tiles_kernel<true><<<grid, 256, 0, s>>>(nbr, (int)filter_size, n_rows, n_in_rows, order, tile_rows, n_uniq, uniq, local, stats);
     else
         plan_tiles_kernel<false><<<grid, 256, 0, s>>>(nbr, (int)filter_size, n_rows, n_in_rows, order, tile_rows, n_uniq, uniq, local, stats);
+    if (tap_mirror != nullptr && n_in_rows == n_rows) {
+        const unsigned g = (unsigned)((filter_size * n_rows + 255) / 256);
+        if (idx64) plan_symmetry_kernel<true><<<g, 256, 0, s>>>(nbr, (int)filter_size, n_rows, tap_mirror, stats + 3);
+        else plan_symmetry_kernel<false><<<g, 256, 0, s>>>(nbr, (int)filter_size, n_rows, tap_mirror, stats + 3);
+    } else {
+        cudaMemsetAsync(stats + 3, 0xff, 4, s);                           // -1: not checked
+    }
     HPL_RETURN_LAST();
 }
 

@@ -13,6 +13,23 @@ constexpr int kPts = 32;   // points per CTA tile
 constexpr int kCh = 64;    // channels per CTA tile
 constexpr int kThreads = 256;
 
+// max |x| of a block -> one RED.MAX on the device scalar (non-negative floats order as unsigned integers)
+__device__ __forceinline__ void block_absmax_to(float m, uint32_t* out) {
+    __shared__ float warp_max[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+    if ((tid & 31) == 0) warp_max[tid >> 5] = m;
+    __syncthreads();
+    if (tid == 0) {
+        const int n_warps = (blockDim.x * blockDim.y + 31) >> 5;
+        for (int w = 1; w < n_warps; ++w) m = fmaxf(m, warp_max[w]);
+        // (the plain read may be stale, but the scalar only grows: skipping is safe and keeps thousands of CTAs from
+        // serialising on one L2 address)
+        if (m > 0.f && __float_as_uint(m) > *reinterpret_cast<volatile uint32_t*>(out)) atomicMax(out, __float_as_uint(m));
+    }
+}
+
 // ---------------------------------------------------------------------------------- splat
 // One CTA: a (64 channel x 32 point) tile of x, staged through shared memory so that the
 // global read is coalesced along points and the RED traffic is 16-byte vectors along channels.
@@ -20,7 +37,8 @@ template <bool I64>
 __global__ void __launch_bounds__(kThreads)
 scatter_rows_kernel(const float* __restrict__ x, const float* __restrict__ bary,
                     const void* __restrict__ off, long long n_points, int channels,
-                    float* __restrict__ rows, long long ld, float* __restrict__ wsum) {
+                    float* __restrict__ rows, long long ld, long long n_rows, float* __restrict__ wsum,
+                    uint32_t* __restrict__ in_amax) {
     __shared__ float tile[kCh][kPts + 1];
     __shared__ float s_bary[4][kPts];
     __shared__ int s_off[4][kPts];
@@ -29,19 +47,25 @@ scatter_rows_kernel(const float* __restrict__ x, const float* __restrict__ bary,
     const int c0 = blockIdx.y * kCh;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
+    float x_max = 0.f;
 #pragma unroll
     for (int i = 0; i < kCh / 8; ++i) {
         const int c = c0 + warp + 8 * i;
         const long long n = n0 + lane;
-        tile[warp + 8 * i][lane] = (c < channels && n < n_points) ? __ldg(x + (long long)c * n_points + n) : 0.f;
+        const float v = (c < channels && n < n_points) ? __ldg(x + (long long)c * n_points + n) : 0.f;
+        tile[warp + 8 * i][lane] = v;
+        x_max = fmaxf(x_max, fabsf(v));
     }
     if (threadIdx.x < 4 * kPts) {
         const int r = threadIdx.x >> 5;
         const long long n = n0 + lane;
         const bool ok = n < n_points;
         s_bary[r][lane] = ok ? __ldg(bary + r * n_points + n) : 0.f;
-        s_off[r][lane] = ok ? load_idx<I64>(off, r * n_points + n) : -1;
+        int row = ok ? load_idx<I64>(off, r * n_points + n) : -1;
+        if (row >= n_rows) row = -1;                     // out-of-range offsets are dropped (the reference would raise)
+        s_off[r][lane] = row;
     }
+    if (in_amax != nullptr) block_absmax_to(x_max, in_amax);   // fused max|x| (operand-scale bound of the splatted rows)
     __syncthreads();
 
     if (wsum != nullptr && blockIdx.y == 0 && threadIdx.x < 4 * kPts) {
@@ -73,7 +97,7 @@ __global__ void __launch_bounds__(kThreads)
 gather_rows_kernel(const float* __restrict__ rows, long long ld, const float* __restrict__ bary,
                    const void* __restrict__ off, const float* __restrict__ scale,
                    const float* __restrict__ bias, long long n_points, int channels,
-                   float* __restrict__ y) {
+                   long long n_rows, float* __restrict__ y) {
     __shared__ float tile[kCh][kPts + 1];
     __shared__ float s_w[4][kPts];
     __shared__ int s_off[4][kPts];
@@ -89,6 +113,7 @@ gather_rows_kernel(const float* __restrict__ rows, long long ld, const float* __
         float w = 0.f;
         if (n < n_points) {
             row = load_idx<I64>(off, r * n_points + n);
+            if (row >= n_rows) row = -1;
             w = __ldg(bary + r * n_points + n);
             if (scale != nullptr && row >= 0) w *= __ldg(scale + row);
         }
@@ -137,21 +162,6 @@ gather_rows_kernel(const float* __restrict__ rows, long long ld, const float* __
 }
 
 // ------------------------------------------------------------------------------ normalise
-// max |x| of a block -> one RED.MAX on the device scalar (non-negative floats order as unsigned integers)
-__device__ __forceinline__ void block_absmax_to(float m, uint32_t* out) {
-    __shared__ float warp_max[32];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
-    if ((tid & 31) == 0) warp_max[tid >> 5] = m;
-    __syncthreads();
-    if (tid == 0) {
-        const int n_warps = (blockDim.x * blockDim.y + 31) >> 5;
-        for (int w = 1; w < n_warps; ++w) m = fmaxf(m, warp_max[w]);
-        if (m > 0.f) atomicMax(out, __float_as_uint(m));
-    }
-}
-
 __global__ void normalize_rows_kernel(float* __restrict__ rows, long long ld, long long n_rows, int quads,
                                       const float* __restrict__ wsum, float* __restrict__ inv, uint32_t* __restrict__ amax) {
     float m = 0.f;
@@ -322,15 +332,16 @@ int hpl_sm_arch(void) {
 }
 
 int hpl_scatter_rows(const float* x, const float* bary, const void* off, int idx64, int64_t n_points,
-                     int64_t channels, float* rows, int64_t ld, float* wsum, void* stream) {
-    HPL_CHECK_ARG(x && bary && off && rows && n_points >= 0 && channels > 0);
+                     int64_t channels, float* rows, int64_t ld, int64_t n_rows, float* wsum, uint32_t* in_amax,
+                     void* stream) {
+    HPL_CHECK_ARG(x && bary && off && rows && n_points >= 0 && channels > 0 && n_rows >= 0);
     HPL_CHECK_ARG(ld % 4 == 0 && ld >= channels && ((uintptr_t)rows & 15) == 0);
     if (n_points == 0) return 0;
     dim3 grid(blocks_for(n_points, kPts), blocks_for(channels, kCh));
     if (idx64)
-        scatter_rows_kernel<true><<<grid, kThreads, 0, as_stream(stream)>>>(x, bary, off, n_points, (int)channels, rows, ld, wsum);
+        scatter_rows_kernel<true><<<grid, kThreads, 0, as_stream(stream)>>>(x, bary, off, n_points, (int)channels, rows, ld, n_rows, wsum, in_amax);
     else
-        scatter_rows_kernel<false><<<grid, kThreads, 0, as_stream(stream)>>>(x, bary, off, n_points, (int)channels, rows, ld, wsum);
+        scatter_rows_kernel<false><<<grid, kThreads, 0, as_stream(stream)>>>(x, bary, off, n_points, (int)channels, rows, ld, n_rows, wsum, in_amax);
     HPL_RETURN_LAST();
 }
 
@@ -359,16 +370,16 @@ int hpl_normalize_rows_amax(float* rows, int64_t ld, int64_t n_rows, int64_t cha
 }
 
 int hpl_gather_rows(const float* rows, int64_t ld, const float* bary, const void* off, int idx64,
-                    const float* scale, const float* bias, int64_t n_points, int64_t channels, float* y,
-                    void* stream) {
-    HPL_CHECK_ARG(rows && bary && off && y && n_points >= 0 && channels > 0);
+                    const float* scale, const float* bias, int64_t n_points, int64_t channels, int64_t n_rows,
+                    float* y, void* stream) {
+    HPL_CHECK_ARG(rows && bary && off && y && n_points >= 0 && channels > 0 && n_rows >= 0);
     HPL_CHECK_ARG(ld % 4 == 0 && ld >= channels && ((uintptr_t)rows & 15) == 0);
     if (n_points == 0) return 0;
     dim3 grid(blocks_for(n_points, kPts), blocks_for(channels, kCh));
     if (idx64)
-        gather_rows_kernel<true><<<grid, kThreads, 0, as_stream(stream)>>>(rows, ld, bary, off, scale, bias, n_points, (int)channels, y);
+        gather_rows_kernel<true><<<grid, kThreads, 0, as_stream(stream)>>>(rows, ld, bary, off, scale, bias, n_points, (int)channels, n_rows, y);
     else
-        gather_rows_kernel<false><<<grid, kThreads, 0, as_stream(stream)>>>(rows, ld, bary, off, scale, bias, n_points, (int)channels, y);
+        gather_rows_kernel<false><<<grid, kThreads, 0, as_stream(stream)>>>(rows, ld, bary, off, scale, bias, n_points, (int)channels, n_rows, y);
     HPL_RETURN_LAST();
 }
 

@@ -10,15 +10,17 @@ from . import _lib
 
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 
-# Contraction engine: 4 = tcgen05 3xFP16 with operands pre-split once in HBM and moved by TMA row gathers
-# (cp.async.bulk.tensor ... tile::gather4; csrc/gemm_tma.cu; forward / data gradient, dW uses engine 2),
-# 2 = tcgen05 with a scaled FP16 hi/lo split done in registers per tap ("3xFP16", half
-# the operand bytes; default), 3 = same math with operands pre-split once in HBM and copied by cp.async
-# (parity-green, currently slower -- see csrc/gemm_tc16p.cu),
-# 1 = tcgen05 with 3xTF32 compensation, 0 = fp32 FMA on CUDA cores (parity anchor).  All are hand-written
-# sm_100a kernels with fp32-level accuracy; HPL_GEMM_PRECISION overrides the default.
+# Contraction engines (all hand-written sm_100a kernels with fp32-level accuracy; HPL_GEMM_PRECISION overrides):
+#   5 (default) = engine 5 for the gathered first layer of a stack whenever its table has a usable tile plan
+#                 (csrc/plan.cu + gemm_plan.cu: every distinct neighbour row of a 128-vertex tile is staged once,
+#                 pre-split h16b operands, forward / data gradient / weight gradient on the same plan), engine 2
+#                 for everything else (1x1 layers, wide layers, tables without locality);
+#   2 = tcgen05 with a scaled FP16 hi/lo split done in registers per tap ("3xFP16", csrc/gemm_tc16.cu);
+#   4 = tcgen05 3xFP16 with operands pre-split once in HBM and moved by cp.async / TMA row gathers
+#       (csrc/gemm_tma.cu; forward / data gradient, dW uses engine 2);
+#   0 = fp32 FMA on CUDA cores (parity anchor; also takes shapes with C % 4 != 0).
 import os as _os
-DEFAULT_PRECISION = int(_os.environ.get("HPL_GEMM_PRECISION", "2"))
+DEFAULT_PRECISION = int(_os.environ.get("HPL_GEMM_PRECISION", "5"))
 _tc_workspace = {}
 
 
@@ -161,8 +163,9 @@ def alloc_rows(n_rows, channels, device, zero=False):
     return torch.empty((n_rows, ld), dtype=torch.float32, device=device)
 
 
-def scatter_rows(x, bary, off, n_rows, want_wsum):
-    """x (C, N), bary (4, N), off (4, N) -> rows (n_rows, ld) [, wsum (n_rows)]."""
+def scatter_rows(x, bary, off, n_rows, want_wsum, in_amax=None):
+    """x (C, N), bary (4, N), off (4, N) -> rows (n_rows, ld) [, wsum (n_rows)].  in_amax: zeroed slot that receives
+    max|x| (a bound of the normalised splat's magnitude)."""
     _f32(x, "x"); _f32(bary, "bary")
     off, i64 = _idx(off, "off")
     c, n = x.shape
@@ -170,7 +173,8 @@ def scatter_rows(x, bary, off, n_rows, want_wsum):
     wsum = torch.zeros(n_rows, dtype=torch.float32, device=x.device) if want_wsum else None
     with _timed("scatter"):
         _lib.call("hpl_scatter_rows", x.data_ptr(), bary.data_ptr(), off.data_ptr(), i64, n, c,
-                  rows.data_ptr(), rows.stride(0), wsum.data_ptr() if want_wsum else None, _stream())
+                  rows.data_ptr(), rows.stride(0), n_rows, wsum.data_ptr() if want_wsum else None,
+                  in_amax.data_ptr() if in_amax is not None else None, _stream())
     return rows, wsum
 
 
@@ -180,8 +184,12 @@ def amax_slots(device, n):
 
 
 def fused_stats():
-    """True when the default engine takes its operand scales from producer-fused statistics (engine 2)."""
-    return DEFAULT_PRECISION == 2
+    """True when the default engine takes its operand scales from producer-fused statistics (engines 2 / 5)."""
+    return DEFAULT_PRECISION in (2, 5)
+
+
+def engine5_enabled():
+    return DEFAULT_PRECISION == 5
 
 
 def normalize_rows_(rows, channels, wsum, amax=None):
@@ -210,15 +218,6 @@ def absmax(t):
     return out
 
 
-def split16(x, channels, amax):
-    """fp16 hi/lo image of a vertex-major matrix (see include/hplflownet_b200.h: hpl_split16)."""
-    _f32(x, "x")
-    n = x.size(0)
-    buf = torch.empty(_lib.load().hpl_split16_bytes(n, channels), dtype=torch.uint8, device=x.device)
-    _lib.call("hpl_split16", x.data_ptr(), x.stride(0), n, channels, amax.data_ptr(), buf.data_ptr(), _stream())
-    return buf
-
-
 def h16_split(x, channels, amax):
     """fp16 hi/lo row image for the TMA-gathered contraction (include/hplflownet_b200.h: hpl_h16_split)."""
     _f32(x, "x")
@@ -240,11 +239,6 @@ def _dense_permutation(w):
     return True
 
 
-def tc_path(c_in, precision=None):
-    """True when the tensor-core kernels (which can fold ``row_scale``) will run for this operand."""
-    return (DEFAULT_PRECISION if precision is None else precision) >= 1 and c_in % 4 == 0
-
-
 def gather_rows(rows, channels, bary, off, scale=None, bias=None):
     """rows (H, ld) -> y (C, N)."""
     _f32(rows, "rows"); _f32(bary, "bary")
@@ -254,7 +248,7 @@ def gather_rows(rows, channels, bary, off, scale=None, bias=None):
     with _timed("gather"):
         _lib.call("hpl_gather_rows", rows.data_ptr(), rows.stride(0), bary.data_ptr(), off.data_ptr(), i64,
                   scale.data_ptr() if scale is not None else None,
-                  bias.data_ptr() if bias is not None else None, n, channels, y.data_ptr(), _stream())
+                  bias.data_ptr() if bias is not None else None, n, channels, rows.size(0), y.data_ptr(), _stream())
     return y
 
 
@@ -266,6 +260,8 @@ def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_majo
     _f32(x, "x")
     if not (w.is_cuda and w.dtype == torch.float32):
         raise ValueError("w must be a CUDA float32 tensor")
+    if row_scale is not None:
+        raise ValueError("row_scale went away with the 3xTF32 engine: normalise the rows (ops.normalize_rows_)")
     f, c, co = w.shape
     assert c == c_in
     if nbr is not None:
@@ -280,14 +276,12 @@ def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_majo
                else alloc_rows(n_out_rows, co, x.device))
     if precision is None:
         precision = DEFAULT_PRECISION
+    if precision == 5:
+        precision = 2
     bias_ptr = bias.data_ptr() if bias is not None else None
-    if precision == 4 and (c % 4 != 0 or row_scale is not None):
-        precision = 1
-    if precision == 3 and (c % 4 != 0 or row_scale is not None):
-        precision = 1
-    if precision == 2 and (c % 4 != 0 or row_scale is not None):
-        precision = 1
-    if precision == 1 and c % 4 != 0:
+    if precision not in (0, 2, 4):
+        raise ValueError("unknown contraction engine %r" % (precision,))
+    if c % 4 != 0:
         precision = 0
     if precision != 2:
         w = w.contiguous()
@@ -298,15 +292,6 @@ def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_majo
             x16 = h16_split(x, c, x_amax)
         with _timed(tag):
             _lib.call("hpl_blur_gemm_tma", x16.data_ptr(), x.size(0), nbr_ptr, i64, f, n_out_rows, c, co,
-                      w.data_ptr(), bias_ptr, act, out.data_ptr(), out.stride(0), int(out_channel_major),
-                      ws.data_ptr(), x_amax.data_ptr(), _stream())
-    elif precision == 3:
-        ws = _workspace(x.device, _lib.load().hpl_blur_gemm_f16_workspace(f, c, co))
-        if x16 is None:
-            x_amax = absmax(x)
-            x16 = split16(x, c, x_amax)
-        with _timed(tag):
-            _lib.call("hpl_blur_gemm_p16", x16.data_ptr(), x.size(0), nbr_ptr, i64, f, n_out_rows, c, co,
                       w.data_ptr(), bias_ptr, act, out.data_ptr(), out.stride(0), int(out_channel_major),
                       ws.data_ptr(), x_amax.data_ptr(), _stream())
     elif precision == 2:
@@ -322,14 +307,7 @@ def blur_gemm(x, c_in, nbr, n_out_rows, w, bias, act, out=None, out_channel_majo
                       ws.data_ptr(), ws_valid, x_amax.data_ptr(), out_amax.data_ptr() if out_amax is not None else None, _stream())
         commit()
         out_amax = None
-    elif precision == 1:
-        ws = _workspace(x.device, _lib.load().hpl_blur_gemm_tc_workspace(f, c, co))
-        with _timed(tag):
-            _lib.call("hpl_blur_gemm_tc", x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, f, n_out_rows, c, co,
-                      w.data_ptr(), bias_ptr, act, out.data_ptr(), out.stride(0), int(out_channel_major),
-                      ws.data_ptr(), row_scale.data_ptr() if row_scale is not None else None, _stream())
     else:
-        assert row_scale is None, "row_scale is a tensor-core-path feature; normalise the rows instead"
         with _timed(tag):
             _lib.call("hpl_blur_gemm", x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, f, n_out_rows, c, co,
                       w.data_ptr(), bias_ptr, act, out.data_ptr(), out.stride(0), int(out_channel_major), 0,
@@ -343,6 +321,8 @@ def blur_wgrad(x, c_in, nbr, n_out_rows, dz, c_out, filter_size, want_db=True, p
                x_amax=None, dz_amax=None, x16=None, dz16=None):
     """Returns dw (F, C, Co), db (Co)."""
     _f32(x, "x"); _f32(dz, "dz")
+    if row_scale is not None:
+        raise ValueError("row_scale went away with the 3xTF32 engine")
     if nbr is not None:
         nbr, i64 = _idx(nbr, "nbr")
         nbr_ptr = nbr.data_ptr()
@@ -352,24 +332,9 @@ def blur_wgrad(x, c_in, nbr, n_out_rows, dz, c_out, filter_size, want_db=True, p
     db = torch.zeros(c_out, dtype=torch.float32, device=x.device) if want_db else None
     if precision is None:
         precision = DEFAULT_PRECISION
-    if precision == 4:                       # the TMA engine covers forward / data gradient; dW stays register-staged
-        precision, x16, dz16 = 2, None, None
-    if precision == 3 and c_in % 32 == 0 and row_scale is None:
-        if x16 is None:
-            x_amax = absmax(x)
-            x16 = split16(x, c_in, x_amax)
-        if dz16 is None:
-            dz_amax = absmax(dz)
-            dz16 = split16(dz, c_out, dz_amax)
-        with _timed("wgrad"):
-            _lib.call("hpl_blur_wgrad_p16", x16.data_ptr(), x.size(0), nbr_ptr, i64, filter_size, n_out_rows, c_in, c_out,
-                      dz16.data_ptr(), dw.data_ptr(), x_amax.data_ptr(), dz_amax.data_ptr(), _stream())
-            if want_db:
-                _lib.call("hpl_column_sums", dz.data_ptr(), dz.stride(0), n_out_rows, c_out, db.data_ptr(), _stream())
-        return dw, db
-    if precision == 3:
+    if precision in (4, 5):                  # engines 4 / 5 cover other roles; dW of these layers is register-staged
         precision = 2
-    if precision == 2 and c_in % 4 == 0 and row_scale is None:
+    if precision == 2 and c_in % 4 == 0:
         if x_amax is None:
             x_amax = absmax(x)
         if dz_amax is None:
@@ -379,15 +344,17 @@ def blur_wgrad(x, c_in, nbr, n_out_rows, dz, c_out, filter_size, want_db=True, p
                       n_out_rows, c_in, c_out, dz.data_ptr(), dz.stride(0), dw.data_ptr(),
                       db.data_ptr() if want_db else None, x_amax.data_ptr(), dz_amax.data_ptr(), _stream())
         return dw, db
-    tc = precision >= 1 and c_in % 4 == 0
-    assert tc or row_scale is None
-    extra = (row_scale.data_ptr() if row_scale is not None else None,) if tc else ()
-    fn = "hpl_blur_wgrad_tc" if tc else "hpl_blur_wgrad"
     with _timed("wgrad"):
-        _lib.call(fn, x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, filter_size, n_out_rows,
+        _lib.call("hpl_blur_wgrad", x.data_ptr(), x.stride(0), x.size(0), nbr_ptr, i64, filter_size, n_out_rows,
                   c_in, c_out, dz.data_ptr(), dz.stride(0), dw.data_ptr(), db.data_ptr() if want_db else None,
-                  *extra, _stream())
+                  _stream())
     return dw, db
+
+
+def column_sums_(rows, channels, sums):
+    """sums[c] += sum_v rows[v, c] (sums zeroed by the caller)."""
+    _lib.call("hpl_column_sums", rows.data_ptr(), rows.stride(0), rows.size(0), channels, sums.data_ptr(), _stream())
+    return sums
 
 
 def act_backward_stats_(dz, y, channels, act, amax=None, colsum=None):
@@ -461,18 +428,10 @@ def conv5_supported(filter_size, c_in, c_out):
     return bool(_lib.load().hpl_conv5_supported(filter_size, c_in, c_out))
 
 
-_tap_maps = {}
-
-
 def _mirror_map(filter_size, device):
-    key = (filter_size, device)
-    t = _tap_maps.get(key)
-    if t is None:
-        from . import plans
-        m = plans.mirror_taps(filter_size)
-        t = torch.tensor(m, dtype=torch.int32, device=device) if m is not None else False
-        _tap_maps[key] = t
-    return t
+    from . import plans
+    t = plans._mirror_tensor(filter_size, device)
+    return t if t is not None else False
 
 
 def conv5(x16, plan, c_in, w, bias, act, x_amax, out=None, out_amax=None, mirror=False, tag="fwd"):

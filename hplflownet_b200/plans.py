@@ -49,15 +49,27 @@ def mirror_taps(filter_size):
     return [index[tuple((-o).tolist())] for o in offs]
 
 
+_mirrors = {}
+
+
+def _mirror_tensor(filter_size, device):
+    key = (filter_size, device)
+    if key not in _mirrors:
+        m = mirror_taps(filter_size)
+        _mirrors[key] = torch.tensor(m, dtype=torch.int32, device=device) if m is not None else None
+    return _mirrors[key]
+
+
 class TilePlan:
     """Device buffers + host-side facts of one planned table."""
 
     def __init__(self, buf, n_rows, n_in_rows, filter_size, stats, order, sweeps):
         self.buf, self.n_rows, self.n_in_rows, self.filter_size = buf, n_rows, n_in_rows, filter_size
-        self.max_uniq, self.overflow, self.sum_uniq = stats
+        self.max_uniq, self.overflow, self.sum_uniq, violations = stats
         self.order, self.sweeps = order, sweeps
         self.n_tiles = (n_rows + 127) // 128
-        self.symmetric = None          # set by check_symmetric()
+        # True: nbr[mirror(f), nbr[f, v]] == v everywhere, the data gradient may reuse this plan with mirrored taps
+        self.symmetric = violations == 0
 
     @property
     def usable(self):
@@ -114,10 +126,12 @@ def build(nbr2, n_in_rows=None, order="spatial"):
         order, sweeps = spatial_order(nbr2) if order == "spatial" else (None, 0)
     buf = torch.empty(max(L.hpl_plan_bytes(h), 256), dtype=torch.uint8, device=nbr2.device)
     stats = torch.zeros(4, dtype=torch.int32, device=nbr2.device)
+    mirror = _mirror_tensor(f, nbr2.device)
     _lib.call("hpl_plan_build", nbr2.data_ptr(), int(nbr2.dtype == torch.int64), f, h, n_in,
-              order.data_ptr() if order is not None else None, buf.data_ptr(), stats.data_ptr(), _stream())
-    s = stats.tolist()
-    return TilePlan(buf, h, n_in, f, (s[0], s[1], s[2]), order, sweeps)
+              order.data_ptr() if order is not None else None, mirror.data_ptr() if mirror is not None else None,
+              buf.data_ptr(), stats.data_ptr(), _stream())
+    s = stats.tolist()                                      # (one host read per planned table)
+    return TilePlan(buf, h, n_in, f, tuple(s), order, sweeps)
 
 
 def plan_for(nbr2):

@@ -22,10 +22,10 @@ class _PointwiseFunction(torch.autograd.Function):
         xr = ops.cm_to_rows(x[0].contiguous(), amax=x_amax)
         n = xr.size(0)
         layers = [(kernel_weight(params[2 * l]), params[2 * l + 1].detach(), acts[l]) for l in range(len(acts))]
-        xs, chans, out_cm = _stack.forward(xr, c_in, n, layers, None, last_channel_major=True, x_amax=x_amax)
+        xs, chans, out_cm, amaxs = _stack.forward(xr, c_in, n, layers, None, last_channel_major=True, x_amax=x_amax)
         out = out_cm if out_cm is not None else ops.rows_to_cm(xs[-1], chans[-1])
         ctx.xs, ctx.chans, ctx.layers, ctx.n = xs, chans, layers, n
-        ctx.amaxs = _stack.forward.last_amaxs
+        ctx.amaxs = amaxs
         ctx.shapes = [p.shape for p in params]
         return out.unsqueeze(0)
 

@@ -51,11 +51,14 @@ int hpl_sm_arch(void);
 /* SPLAT (scatter half of SparseSum + splat, bilateralNN.py:9-30,150-166; also the backward of
  * SLICE, :226-232):   rows[off[r,n], c] += bary[r,n] * x[c,n]      r < 4
  * and, when wsum != NULL,   wsum[off[r,n]] += bary[r,n]              (:168-182).
- * x (C, N) channel-major; bary (4, N); off (4, N) in [0, H); rows (H, ld) and wsum (H) must be
- * zeroed by the caller (hpl_fill_zero).  Accumulation order is not deterministic (fp32 RED). */
+ * x (C, N) channel-major; bary (4, N); off (4, N) in [0, n_rows) -- entries outside are dropped (the reference
+ * raises an index error); rows (n_rows, ld) and wsum (n_rows) must be zeroed by the caller (hpl_fill_zero).
+ * in_amax (device scalar, may be NULL, zeroed by the caller): receives the bit pattern of max|x| (the operand-scale
+ * bound of the splatted, normalised rows: a convex combination never exceeds it).  Accumulation order is not
+ * deterministic (fp32 RED). */
 int hpl_scatter_rows(const float* x, const float* bary, const void* off, int idx64,
-                     int64_t n_points, int64_t channels, float* rows, int64_t ld, float* wsum,
-                     void* stream);
+                     int64_t n_points, int64_t channels, float* rows, int64_t ld, int64_t n_rows,
+                     float* wsum, uint32_t* in_amax, void* stream);
 
 /* Density normalisation (bilateralNN.py:185-186):  inv[v] = 1/(wsum[v] + 1e-5),
  * rows[v, :] *= inv[v].  inv may alias wsum.  rows == NULL: only the reciprocal is computed (the
@@ -65,10 +68,10 @@ int hpl_normalize_rows(float* rows, int64_t ld, int64_t n_rows, int64_t channels
 
 /* SLICE (bilateralNN.py:226-236; also the backward of SPLAT, :33-40):
  *   y[c,n] = sum_r bary[r,n] * scale[off[r,n]] * rows[off[r,n], c]  (+ bias[c])
- * scale (H) and bias (C) may be NULL. y (C, N) channel-major. */
+ * scale (H) and bias (C) may be NULL. y (C, N) channel-major.  off entries outside [0, n_rows) read zeros. */
 int hpl_gather_rows(const float* rows, int64_t ld, const float* bary, const void* off, int idx64,
                     const float* scale, const float* bias, int64_t n_points, int64_t channels,
-                    float* y, void* stream);
+                    int64_t n_rows, float* y, void* stream);
 
 /* BLUR / learned convolution over lattice neighbours (bilateralNN.py:198-221 with the conv
  * built at :94-113), as a gather-GEMM with fused bias + activation:
@@ -86,19 +89,6 @@ int hpl_blur_gemm(const float* in, int64_t ld_in, int64_t n_in_rows, const void*
                   const float* w, const float* bias, int act, float* out, int64_t ld_out,
                   int out_channel_major, int precision, void* stream);
 
-/* Same contract as hpl_blur_gemm on the tcgen05 tensor cores with 3xTF32 error compensation
- * (fp32-level accuracy: every operand is split hi + lo in TF32, three MMAs per K step, fp32
- * accumulation in tensor memory).  `workspace` holds the pre-split weight image and must be
- * hpl_blur_gemm_tc_workspace(F, C, Co) bytes, 16-byte aligned; it is written by this call.
- * row_scale (n_in_rows floats, may be NULL): every gathered row r is multiplied by row_scale[r]
- * on the fly -- the density normalisation 1/(wsum+1e-5) of bilateralNN.py:185-186 without a
- * separate pass over the lattice. */
-int64_t hpl_blur_gemm_tc_workspace(int64_t filter_size, int64_t c_in, int64_t c_out);
-int hpl_blur_gemm_tc(const float* in, int64_t ld_in, int64_t n_in_rows, const void* nbr, int idx64,
-                     int64_t filter_size, int64_t n_out_rows, int64_t c_in, int64_t c_out,
-                     const float* w, const float* bias, int act, float* out, int64_t ld_out,
-                     int out_channel_major, float* workspace, const float* row_scale, void* stream);
-
 /* Weight gradient of the layer above:
  *   dw[f, c, o] += sum_v in[nbr[f,v], c] * dz[v, o]        db[o] += sum_v dz[v, o]
  * dw (F, C, Co) and db (Co, may be NULL) must be zeroed by the caller; partial sums over
@@ -107,15 +97,8 @@ int hpl_blur_wgrad(const float* in, int64_t ld_in, int64_t n_in_rows, const void
                    int64_t filter_size, int64_t n_out_rows, int64_t c_in, int64_t c_out,
                    const float* dz, int64_t ld_dz, float* dw, float* db, void* stream);
 
-/* Same contract as hpl_blur_wgrad on the tcgen05 tensor cores (3xTF32, see hpl_blur_gemm_tc).
- * Requires c_in % 4 == 0.  row_scale as in hpl_blur_gemm_tc. */
-int hpl_blur_wgrad_tc(const float* in, int64_t ld_in, int64_t n_in_rows, const void* nbr, int idx64,
-                      int64_t filter_size, int64_t n_out_rows, int64_t c_in, int64_t c_out,
-                      const float* dz, int64_t ld_dz, float* dw, float* db, const float* row_scale,
-                      void* stream);
-
-/* "3xFP16" variants of the two tensor-core contractions (csrc/gemm_tc16.cu): same contracts and
- * the same fp32-level accuracy as the 3xTF32 kernels, half the operand bytes through shared memory.
+/* "3xFP16" tensor-core variants of the two contractions (csrc/gemm_tc16.cu, tcgen05 with fp32 accumulation in
+ * tensor memory): same contracts, fp32-level accuracy (three MMAs per K step: hi.hi + hi.lo + lo.hi).
  * Operands are split hi + lo*2^-11 in FP16 after scaling by a per-tensor power of two derived from
  * max|x|, which the caller provides as a DEVICE scalar holding the fp32 bit pattern of max|x|:
  *   hpl_absmax(x, count, out_bits)      out_bits <- bits(max_i |x[i]|), x 16-byte aligned
@@ -132,26 +115,6 @@ int hpl_blur_wgrad_f16(const float* in, int64_t ld_in, int64_t n_in_rows, const 
                        int64_t filter_size, int64_t n_out_rows, int64_t c_in, int64_t c_out,
                        const float* dz, int64_t ld_dz, float* dw, float* db, const uint32_t* in_amax,
                        const uint32_t* dz_amax, void* stream);
-
-/* "Split once, copy many" variants (csrc/gemm_tc16p.cu): the operands of the 3xFP16 contractions are
- * pre-split in HBM so the kernels only copy (cp.async) instead of re-splitting every element per tap.
- *   hpl_split16(x, ld, n_rows, C, amax, x16): x16 = n_rows * ceil(C/32) lines of 128 bytes,
- *     line = [32 hi halves | 32 lo halves] of one 32-channel block; hpl_split16_bytes gives the size;
- *     x16 must be 128-byte aligned.
- *   hpl_blur_gemm_p16 / hpl_blur_wgrad_p16: same contracts as the _f16 entry points with `in` (and `dz`)
- *     replaced by their split images.  wgrad requires c_in % 32 == 0.  The forward workspace is
- *     hpl_blur_gemm_f16_workspace(F, C, Co) bytes. */
-int64_t hpl_split16_bytes(int64_t n_rows, int64_t channels);
-int hpl_split16(const float* x, int64_t ld, int64_t n_rows, int64_t channels, const uint32_t* amax,
-                void* x16, void* stream);
-int hpl_blur_gemm_p16(const void* in16, int64_t n_in_rows, const void* nbr, int idx64,
-                      int64_t filter_size, int64_t n_out_rows, int64_t c_in, int64_t c_out,
-                      const float* w, const float* bias, int act, float* out, int64_t ld_out,
-                      int out_channel_major, void* workspace, const uint32_t* in_amax, void* stream);
-int hpl_blur_wgrad_p16(const void* in16, int64_t n_in_rows, const void* nbr, int idx64,
-                       int64_t filter_size, int64_t n_out_rows, int64_t c_in, int64_t c_out,
-                       const void* dz16, float* dw, const uint32_t* in_amax, const uint32_t* dz_amax,
-                       void* stream);
 
 /* Fused statistics (one pass instead of three over the same rows).  `amax` slots are device scalars holding the
  * bit pattern of max|x| (as hpl_absmax writes it); the caller zeroes them, the kernels RED.MAX into them.
@@ -206,13 +169,15 @@ int hpl_blur_gemm_tma(const void* in16, int64_t n_in_rows, const void* nbr, int 
  * table alone by propagating lattice coordinates (coord(nbr[f,v]) = coord(v) + offsets[f], offsets (F,4) int32 =
  * transforms.py:112-130) and sorting along a Morton curve.  stats (4 x int32, device): [0] max distinct rows of a
  * tile, [1] tiles above hpl_plan_umax() (such a plan must not be used: take hpl_blur_gemm_f16), [2] sum of distinct
- * rows over tiles. */
+ * rows over tiles, [3] entries violating nbr[tap_mirror[f], nbr[f,v]] == v (tap_mirror: device, F int32, the tap with the
+ * opposite offset; NULL or n_in_rows != n_rows: -1 = not checked).  0 means the data gradient may run on the same plan
+ * with mirrored taps instead of a transposed table. */
 int64_t hpl_plan_tiles(int64_t n_rows);
 int64_t hpl_plan_umax(void);
 int64_t hpl_plan_offset(int64_t n_rows, int which);
 int64_t hpl_plan_bytes(int64_t n_rows);
 int hpl_plan_build(const void* nbr, int idx64, int64_t filter_size, int64_t n_rows, int64_t n_in_rows,
-                   const int32_t* order, void* plan, int32_t* stats, void* stream);
+                   const int32_t* order, const int32_t* tap_mirror, void* plan, int32_t* stats, void* stream);
 int64_t hpl_plan_order_workspace(int64_t n_rows);
 int hpl_plan_order(const void* nbr, int idx64, int64_t filter_size, int64_t n_rows, const int32_t* offsets,
                    int iterations, void* workspace, int32_t* order, int32_t* changed_out, void* stream);
@@ -273,18 +238,20 @@ int hpl_channel_sums(const float* x, int64_t channels, int64_t n, float* sums, v
  * (hpl_blur_gemm, nbr = NULL) giving t1 (H1, P*width) and t2 (H2, P*width); this call then forms
  *   z[v*F + f, :] = act(bias + sum_p t1[i1[p,v], p*width:(p+1)*width]
  *                            + sum_p t2[i2[f,p,v], p*width:(p+1)*width])
+ * (n1 / n2: rows of t1 / t2; table entries outside [0, n) read zeros)
  * i1 (P, H1) = pc1_corr_indices, i2 (F, P, H1) = pc2_corr_indices, -1 reads zeros.
  * z (H1*F, ldz): row v*F+f, so the same memory is the (H1, F*ldz) operand of the displacement
  * filter (:205).  width % 4 == 0. */
 int hpl_corr_gather(const float* t1, int64_t ld1, const void* i1, const float* t2, int64_t ld2,
                     const void* i2, int idx64, const float* bias, int act, float* z, int64_t ldz,
-                    int64_t width, int64_t patch, int64_t filt, int64_t h1, void* stream);
+                    int64_t width, int64_t patch, int64_t filt, int64_t h1, int64_t n1, int64_t n2,
+                    void* stream);
 
 /* Backward of hpl_corr_gather w.r.t. t1 and t2 (fp32 RED into zeroed dt1 / dt2):
  *   dt2[i2[f,p,v], p, :] += dz[v*F+f, :]      dt1[i1[p,v], p, :] += sum_f dz[v*F+f, :] */
 int hpl_corr_scatter(const float* dz, int64_t ldz, const void* i1, const void* i2, int idx64,
                      float* dt1, int64_t ld1, float* dt2, int64_t ld2, int64_t width, int64_t patch,
-                     int64_t filt, int64_t h1, void* stream);
+                     int64_t filt, int64_t h1, int64_t n1, int64_t n2, void* stream);
 
 /* ---------------------------------------------------------------- index half
  * GPU replacement of GenerateDataUnsymmetric + build_unsymmetric + khash

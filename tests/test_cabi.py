@@ -39,7 +39,7 @@ def test_library_identifies_itself():
 def test_argument_errors_are_reported_without_a_gpu():
     # null pointers / bad leading dimension are rejected before any CUDA call
     lib = _lib.load()
-    assert lib.hpl_scatter_rows(None, None, None, 1, 8, 4, None, 4, None, None) == -1
+    assert lib.hpl_scatter_rows(None, None, None, 1, 8, 4, None, 4, 8, None, None, None) == -1
     with pytest.raises(_lib.HplError):
         _lib.call("hpl_normalize_rows", None, 4, 1, 4, None, None, None)
 

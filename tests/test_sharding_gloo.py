@@ -78,9 +78,12 @@ def _grad_worker(rank, world, port, out_dir):
     frozen = torch.nn.Parameter(torch.ones(4), requires_grad=False)
     x = torch.full((2, 5), float(rank + 1))
     net(x).sum().backward()
-    net[1].bias.grad = None                                  # a parameter without gradient on this rank
+    net[1].bias.grad = None                                  # a parameter without gradient on ANY rank: stays None
+    if rank == 1:
+        net[0].bias.grad = None                              # ... on one rank only: averaged with zeros
     n = allreduce_mean_grads_(list(net.parameters()) + [frozen])
-    torch.save({"n": n, "grads": [p.grad.clone() for p in net.parameters()]}, os.path.join(out_dir, "g%d.pt" % rank))
+    torch.save({"n": n, "grads": [None if p.grad is None else p.grad.clone() for p in net.parameters()]},
+               os.path.join(out_dir, "g%d.pt" % rank))
     dist.destroy_process_group()
 
 
@@ -90,7 +93,7 @@ def test_flat_gradient_allreduce_averages_over_ranks(tmp_path):
     res = [torch.load(tmp_path / ("g%d.pt" % r)) for r in range(world)]
     assert res[0]["n"] == 5 * 7 + 7 + 7 * 3 + 3
     for a, b in zip(res[0]["grads"], res[1]["grads"]):
-        assert torch.equal(a, b)                             # identical on every rank after the all-reduce
+        assert (a is None and b is None) or torch.equal(a, b)    # identical on every rank after the all-reduce
     # expected: mean over ranks of the single-rank gradients (inputs 1 and 2 -> weight grads scale linearly)
     torch.manual_seed(0)
     net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
@@ -100,6 +103,8 @@ def test_flat_gradient_allreduce_averages_over_ranks(tmp_path):
         net(torch.full((2, 5), float(r + 1))).sum().backward()
         grads.append([p.grad.clone() for p in net.parameters()])
     want = [(a + b) / 2 for a, b in zip(*grads)]
-    want[3] = torch.zeros_like(want[3])                      # bias grad was dropped on both ranks -> zeros
-    for got, w in zip(res[0]["grads"], want):
-        assert torch.allclose(got, w, rtol=1e-6, atol=1e-7)
+    want[1] = grads[0][1] / 2                                # rank 1 had no gradient for net[0].bias: mean with zeros
+    assert res[0]["grads"][3] is None                        # dropped on both ranks: the optimizer must skip it (reference semantics)
+    for k, (got, w) in enumerate(zip(res[0]["grads"], want)):
+        if k != 3:
+            assert torch.allclose(got, w, rtol=1e-6, atol=1e-7)

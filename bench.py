@@ -28,9 +28,6 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 METRIC = "point-clouds/sec (BCL fwd+bwd, 8192 pts, d=3, 64ch)"
-# dram__bytes_read.sum + dram__bytes_write.sum of one gather_gemm_f16_kernel (forward) launch on this workload
-# (ncu --set full, profiles/r01b_summary.md: 91.5 + 28.8 MB); algorithmic bytes are ~139 MB.
-NCU_TRAFFIC_BYTES = 120.3e6
 N_POINTS, CHANNELS, SCALE = 8192, 64, 1.0
 
 
@@ -189,31 +186,34 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------ our arm
-def run_ours(args):
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` on this workload, from the committed ncu
+    summary (profiles/ncu_traffic.json, written from an `ncu --set full` capture; null when the kernel is not in it)."""
+    p = os.path.join(REPO, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p))
+    e = d.get(kernel)
+    return (e["dram_bytes"], e.get("source")) if e else (None, None)
+
+
+def make_batch(dev, cloud_ids, scale=SCALE):
+    """Concatenated tables of the given clouds + features / output gradient, resident on `dev`; host copies pinned."""
     import torch
-    import torch.distributed as dist
-    import hplflownet_b200 as hpl
-    from hplflownet_b200 import _lib, ops
     from hplflownet_b200.batching import concat_lattices
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    from hplflownet_b200 import sharding
-    numa_node = sharding.bind_to_gpu_numa_node(local) if world > 1 else None      # before any pinned allocation
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    B = args.clouds
-
-    # ---- synthetic batch: B distinct clouds for this rank (weak scaling: B per GPU)
-    mod = make_state().to(dev)
-    from hplflownet_b200 import sharding
-    items = [cloud_tables(s) for s in sharding.cloud_ids(rank, world, B)]
+    global _GEN
+    if scale != SCALE:
+        saved, _GEN = _GEN, None
+        A = type("A", (), {"dim": 3, "scales_filter_map": [[scale, 1, -1, -1]]})
+        from hplflownet_b200.transforms import GenerateDataUnsymmetric
+        _GEN = GenerateDataUnsymmetric(A())
+        items = [cloud_tables(s) for s in cloud_ids]
+        _GEN = saved
+    else:
+        items = [cloud_tables(s) for s in cloud_ids]
     batch = concat_lattices(items)
     n_tot, h_tot = sum(batch["point_counts"]), sum(batch["vertex_counts"])
-    torch.manual_seed(1000 + rank)
+    torch.manual_seed(1000 + cloud_ids[0])
     host = {
         "features": torch.randn(1, CHANNELS, n_tot).pin_memory(),
         "barycentric": batch["barycentric"].pin_memory(),
@@ -223,15 +223,52 @@ def run_ours(args):
     gy = torch.randn(1, CHANNELS, n_tot, device=dev)
     resident = {k: v.to(dev) for k, v in host.items()}
     resident["features"].requires_grad_(True)
+    return host, resident, gy, n_tot, h_tot
+
+
+def time_steps(fn, steps, warmup, barrier):
+    import torch
+    for _ in range(warmup):
+        fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import hplflownet_b200 as hpl
+    from hplflownet_b200 import _lib, ops, plans, sharding
+    from hplflownet_b200.graphs import GraphedStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    numa_node = sharding.bind_to_gpu_numa_node(local) if world > 1 else None      # before any pinned allocation
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.clouds
+
+    # ---- synthetic batch: B distinct clouds for this rank (weak scaling: B per GPU)
+    mod = make_state().to(dev)
+    host, resident, gy, n_tot, h_tot = make_batch(dev, sharding.cloud_ids(rank, world, B))
     params = list(mod.parameters())
 
-    def fwd_bwd(t):
+    def fwd_bwd(t=resident, g=gy):
         for p in params:
             p.grad = None
         t["features"].grad = None
         y = mod(t["features"], t["barycentric"], t["lattice_offset"], t["blur_neighbors"],
                 t["barycentric"], t["lattice_offset"])
-        y.backward(gy)
+        y.backward(g)
         return y
 
     def barrier():
@@ -239,46 +276,67 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: inputs resident (the clock sampler starts before warm-up: nvidia-smi needs ~100 ms to
-    # deliver its first sample, and warm-up is the same load)
-    # The headline loops rebuild the weight images on every call (the per-parameter image cache of ops.py would skip
-    # two small kernels per GEMM because the weights never change here); the model / training legs below use the cache
-    # the way a deployment does (evaluation: constant weights; training: one rebuild per optimisation step).
-    ops.WEIGHT_CACHE = False
+    # ---- value: inputs resident in HBM.  The tables of the resident batch are planned once, outside the timed region
+    # (a per-lattice precomputation like the tables themselves; csrc/plan.cu).  The headline loops rebuild the weight
+    # images on every call (ops.weight_cache_scope would skip two small kernels per GEMM because the weights never change
+    # here; the number stays conservative).
+    t0 = time.perf_counter()
+    plan = plans.prepare(resident["blur_neighbors"])
+    torch.cuda.synchronize()
+    plan_ms = 1e3 * (time.perf_counter() - t0)
     sampler = ClockSampler(local)
     if rank == 0 and os.environ.get("HPL_BENCH_NO_SMI") != "1":
-        sampler.start()
-    for _ in range(args.warmup):
-        fwd_bwd(resident)
-    barrier()
-    ops.PROFILE_GEMM = []
+        sampler.start()                                  # (nvidia-smi needs ~100 ms for its first sample; warm-up is the same load)
     _lib.launch_count = 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    profiling = os.environ.get("HPL_BENCH_PROFILE") == "1"      # ncu --profile-from-start off: launch list of the timed loop
-    if profiling:
-        torch.cuda.profiler.start()
-    e0.record()
-    for _ in range(args.steps):
-        fwd_bwd(resident)
-    e1.record()
-    barrier()
-    if profiling:
-        torch.cuda.profiler.stop()
-    ms = e0.elapsed_time(e1)
-    launches = _lib.launch_count
-    gemm_events = ops.PROFILE_GEMM
-    ops.PROFILE_GEMM, ops.PROFILE_ROWS = [], True            # separate, untimed pass: CUDA events around splat / slice too
+    fwd_bwd()
+    launches_per_step = _lib.launch_count
+    eager_ms = time_steps(fwd_bwd, args.steps, args.warmup, barrier)
+    # the same step as ONE CUDA-graph launch (every kernel of the forward and the backward on the capturing stream)
+    graph_ms, graph_err = None, None
+    try:
+        graphed = GraphedStep(fwd_bwd)
+        profiling = os.environ.get("HPL_BENCH_PROFILE") == "1"  # ncu --profile-from-start off: launch list of the timed loop
+        barrier()
+        if profiling:
+            torch.cuda.profiler.start()
+        graph_ms = time_steps(graphed.replay, args.steps, args.warmup, barrier)
+        if profiling:
+            torch.cuda.profiler.stop()
+    except Exception as e:                               # noqa: BLE001 -- fall back to the eager number
+        graph_err = "%s: %s" % (type(e).__name__, e)
+        torch.cuda.synchronize()
+    ms = graph_ms if graph_ms is not None else eager_ms
+    # separate, untimed pass: CUDA events around the contraction and the splat / slice kernels
+    ops.PROFILE_GEMM, ops.PROFILE_ROWS = [], True
     for _ in range(5):
-        fwd_bwd(resident)
+        fwd_bwd()
     torch.cuda.synchronize()
-    gemm_events = gemm_events + [e for e in ops.PROFILE_GEMM if e[0] in ("scatter", "gather")]
+    gemm_events = ops.PROFILE_GEMM
     ops.PROFILE_GEMM, ops.PROFILE_ROWS = None, False
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- latency of ONE cloud (the reference's B = 1 usage) and the scale-3.0 point (H ~ 26-31 k per cloud)
+    extra = {}
+    if rank == 0:
+        for name, ids, scale in (("latency_1cloud", [900], SCALE), ("cfg2_scale3", list(range(700, 708)), 3.0)):
+            try:
+                _, res1, gy1, n1, h1 = make_batch(dev, ids, scale)
+                plans.prepare(res1["blur_neighbors"])
+                f1 = lambda: fwd_bwd(res1, gy1)          # noqa: E731
+                e_ms = time_steps(f1, 20, 5, torch.cuda.synchronize) / 20
+                g1 = GraphedStep(f1)
+                g_ms = time_steps(g1.replay, 50, 5, torch.cuda.synchronize) / 50
+                extra[name] = {"clouds": len(ids), "scale": scale, "H": h1, "ms_graph": g_ms, "ms_eager": e_ms,
+                               "clouds_per_s": len(ids) / (g_ms * 1e-3)}
+                del g1, res1, gy1
+            except Exception as e:                       # noqa: BLE001
+                extra[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+        torch.cuda.synchronize()
+
     # ---- e2e: host (pinned) inputs; every step uploads its own inputs H2D and reads its loss + parameter
     # gradients back D2H, all inside the timed region.  The upload of step i+1 is enqueued on a copy stream
-    # before step i computes (what a pin_memory DataLoader does), so PCIe and the SMs overlap.
+    # before step i computes (what a pin_memory DataLoader does), so PCIe and the SMs overlap.  Tables that arrive
+    # fresh every step are not planned (plans.py: a table is planned on its second use), so this path runs engine 2.
     copy_stream = torch.cuda.Stream(device=dev)
 
     def e2e_run(n_steps, host=host):
@@ -327,13 +385,22 @@ def run_ours(args):
     barrier()
     e2e32_s = time.perf_counter() - t0
     h2d32 = sum(v.numel() * v.element_size() for v in host32.values())
+    # host -> device copy ceiling of this rank while every rank uploads (explains the e2e scaling: the ranks share the
+    # host's memory / PCIe fabric)
+    big = host["features"]
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        big.to(dev, non_blocking=True)
+    barrier()
+    h2d_gbs_rank = 10 * big.numel() * 4 / (time.perf_counter() - t0) / 1e9
 
     # ---- secondary, all ranks: data-parallel HPLFlowNet training step (BASELINE configs[4])
-    ops.WEIGHT_CACHE = True
     train = train_leg(dev, rank, world)
 
     # ---- max over ranks
-    ms, e2e_s, e2e32_s = sharding.max_over_ranks([ms, e2e_s, e2e32_s], device=dev)
+    ms, eager_ms, e2e_s, e2e32_s = sharding.max_over_ranks([ms, eager_ms, e2e_s, e2e32_s], device=dev)
+    (h2d_gbs_min,) = sharding.max_over_ranks([-h2d_gbs_rank], device=dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -342,10 +409,10 @@ def run_ours(args):
     value = sharding.job_throughput(B * args.steps, world, ms * 1e-3)
     e2e_value = sharding.job_throughput(B * e2e_steps, world, e2e_s)
 
-    # ---- roofline of the dominant kernel: the blur gather-GEMM (forward launch), tcgen05 3xTF32.
+    # ---- roofline of the dominant kernel: the blur contraction (forward launch), tcgen05 3xFP16.
     # achieved = algorithmic FLOPs (2*F*C*Co per vertex) / CUDA-event duration on the launch
-    # stream; peak = measured dense bf16 tensor throughput (MEASURED_PEAKS.json, burst).  A 3xTF32
-    # contraction issues 3 MMAs per algorithmic MAC: ceiling peak/3 in FP16 (3xFP16), peak/6 in TF32.
+    # stream; peak = measured dense bf16 tensor throughput (MEASURED_PEAKS.json, burst).  A 3xFP16
+    # contraction issues 3 MMA-equivalents per algorithmic MAC: ceiling peak/3.
     peaks = measured_peaks()
     by_tag = {}
     for tag, a, b in gemm_events:
@@ -355,36 +422,46 @@ def run_ours(args):
     gemm_flops = 2.0 * 15 * CHANNELS * CHANNELS * h_tot
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
     fb, bb = algorithmic_bytes(n_tot, h_tot, CHANNELS, CHANNELS)
-    all_gemm_ms = sum(a.elapsed_time(b) for t, a, b in gemm_events if t in ("fwd", "dgrad", "wgrad")) / args.steps
+    all_gemm_ms = sum(avg.get(t, 0.0) for t in ("fwd", "dgrad", "wgrad"))
+    big_five_ms = all_gemm_ms + 2 * avg.get("scatter", 0.0) + 2 * avg.get("gather", 0.0)
     # the bandwidth-bound kernels of the step against the measured HBM copy peak (algorithmic bytes, SURVEY 8d:
     # splat / slice-backward scatter 4(N C + 2 d1 N + H C), slice / splat-backward gather 4(H C + 2 d1 N + N C))
     row_bytes = 4.0 * (n_tot * CHANNELS + 8 * n_tot + h_tot * CHANNELS)
     hbm_kernels = {}
-    for tag, kernel in (("scatter", "scatter_rows_kernel (splat fwd, slice bwd)"), ("gather", "gather_rows_kernel (slice fwd, splat bwd)")):
+    for tag, kernel in (("scatter", "scatter_rows_kernel"), ("gather", "gather_rows_kernel")):
         if tag in avg:
             gbs = row_bytes / (avg[tag] * 1e-3) / 1e9
+            traffic, _ = ncu_traffic(kernel)
             hbm_kernels[tag] = {"kernel": kernel, "kernel_ms": avg[tag], "algorithmic_bytes": row_bytes, "achieved_gbs": gbs,
-                                "peak_gbs": peaks["hbm_gbs"], "frac": gbs / peaks["hbm_gbs"]}
-    engine = {4: "tcgen05 3xFP16, persistent, operands pre-split in HBM, staged by cp.async / TMA",
-              3: "tcgen05 3xFP16, operands pre-split in HBM + cp.async producers", 2: "tcgen05 3xFP16 (scaled hi/lo split)",
-              1: "tcgen05 3xTF32", 0: "fp32 CUDA-core FMA"}[ops.DEFAULT_PRECISION]
-    kname = {4: "gather_gemm_tma_kernel", 3: "gather_gemm_p16_kernel", 2: "gather_gemm_f16_kernel",
-             1: "gather_gemm_tc_kernel", 0: "gather_gemm_kernel"}[ops.DEFAULT_PRECISION]
+                                "peak_gbs": peaks["hbm_gbs"], "frac": gbs / peaks["hbm_gbs"], "traffic": traffic}
+    engine = {5: "tcgen05 3xFP16 on a per-lattice tile plan: distinct neighbour rows staged once per 128-vertex tile, "
+                 "pre-split operands, 2 MMAs per K step",
+              4: "tcgen05 3xFP16, persistent, operands pre-split in HBM, staged by cp.async / TMA",
+              2: "tcgen05 3xFP16 (scaled hi/lo split)", 0: "fp32 CUDA-core FMA"}[ops.DEFAULT_PRECISION]
+    kname = {5: "conv5_kernel", 4: "gather_gemm_tma_kernel", 2: "gather_gemm_f16_kernel",
+             0: "gather_gemm_kernel"}[ops.DEFAULT_PRECISION]
+    if ops.DEFAULT_PRECISION == 5 and not plan.usable:
+        kname, engine = "gather_gemm_f16_kernel", "tcgen05 3xFP16 (scaled hi/lo split); the table has no usable tile plan"
+    traffic, traffic_src = ncu_traffic(kname)
+    step_ms = ms / args.steps
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-        "frac": achieved / peaks["bf16_tflops"], "traffic": NCU_TRAFFIC_BYTES, "peak_source": peaks["source"],
+        "frac": achieved / peaks["bf16_tflops"], "traffic": traffic, "traffic_source": traffic_src,
+        "peak_source": peaks["source"],
         "kernel": "%s (blur forward, %s)" % (kname, engine),
         "kernel_ms": gemm_ms, "kernel_ms_by_role": avg,
-        "frac_of_3_mma_ceiling": achieved / (peaks["bf16_tflops"] / (3.0 if ops.DEFAULT_PRECISION >= 2 else 6.0)),
+        "frac_of_3_mma_ceiling": achieved / (peaks["bf16_tflops"] / 3.0),
+        "by_role_frac_of_3_mma_ceiling": {t: gemm_flops / (avg[t] * 1e-3) / 1e12 / (peaks["bf16_tflops"] / 3.0)
+                                          for t in ("fwd", "dgrad", "wgrad") if t in avg},
         "kernel_algorithmic_bytes": blur_fwd_bytes(h_tot, CHANNELS, CHANNELS),
         "kernel_algorithmic_gbs": blur_fwd_bytes(h_tot, CHANNELS, CHANNELS) / (gemm_ms * 1e-3) / 1e9,
-        "contraction_share_of_step": all_gemm_ms / (ms / args.steps),
-        "whole_step_algorithmic_gbs": (fb + bb) / (ms / args.steps * 1e-3) / 1e9,
-        "whole_step_frac_of_hbm_peak": (fb + bb) / (ms / args.steps * 1e-3) / 1e9 / peaks["hbm_gbs"],
+        "contraction_share_of_step": all_gemm_ms / step_ms,
+        "step_minus_big_five_ms": step_ms - big_five_ms,
+        "whole_step_algorithmic_gbs": (fb + bb) / (step_ms * 1e-3) / 1e9,
+        "whole_step_frac_of_hbm_peak": (fb + bb) / (step_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
         "hbm_bound_kernels": hbm_kernels,
-        "note": "dense fp32-accurate contraction (AI ~205 FLOP/B) -> tensor-bound by the roofline, not HBM-bound; in practice "
-                "paced by the L2->SM gather of the 15x re-read operand (~5.8 TB/s whatever the staging mechanism: LDG+STS, "
-                "cp.async or TMA gather4 -- ablations in profiles/r01b_summary.md); ncu: tensor pipe ~19% active, L2 hit 83%",
+        "note": "dense fp32-accurate contraction (AI ~205 FLOP/B) -> tensor-bound by the roofline, not HBM-bound; engine 5 is "
+                "paced by the SM's shared-memory port (staged rows -> operand tiles -> tensor core), see DESIGN.md 3.2c",
     }
 
     cpu = cpu_baseline_leg()
@@ -394,7 +471,7 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "BilateralConvFlex(3,1,64,[64]) fwd+bwd, 8192-pt frustum clouds, scale 1.0, "
                                "%d distinct clouds per GPU per step concatenated (reference is B=1)" % B,
@@ -402,15 +479,27 @@ def run_ours(args):
                    "l2_policy": "inputs larger than L2 (working set %.0f MB per step)" % (
                        4e-6 * (2 * n_tot * CHANNELS + 2 * h_tot * CHANNELS)),
                    "index_dtype": "int64 (reference format)",
+                   "launch": ("one CUDA-graph replay per step (forward + backward captured through the module API)"
+                              if graph_ms is not None else "eager (graph capture failed: %s)" % graph_err),
+                   "tile_plan": {"built_once_ms": plan_ms, "relaxation_sweeps": plan.sweeps, "tiles": plan.n_tiles,
+                                 "mean_distinct_rows_per_tile": plan.sum_uniq / max(plan.n_tiles, 1),
+                                 "max_distinct_rows_per_tile": plan.max_uniq, "usable": plan.usable,
+                                 "note": "per-lattice precomputation from blur_neighbors alone, outside the timed region"},
                    "weight_images": "rebuilt on every call in the timed loops (cache disabled)",
                    "numa_node_rank0": numa_node},
+        "eager": {"value": sharding.job_throughput(B * args.steps, world, eager_ms * 1e-3), "ms_per_step": eager_ms / args.steps,
+                  "note": "same step launched kernel by kernel from Python"},
+        "latency_1cloud_ms": extra.get("latency_1cloud", {}).get("ms_graph"),
+        "latency_1cloud": extra.get("latency_1cloud"), "cfg2_scale3": extra.get("cfg2_scale3"),
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "clouds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps,
+                "steps": e2e_steps, "aggregate_h2d_gbs": world * h2d * e2e_steps / e2e_s / 1e9,
+                "h2d_copy_ceiling_gbs_per_rank_all_ranks_busy": -h2d_gbs_min,
                 "int32_tables": {"value": sharding.job_throughput(B * e2e_steps, world, e2e32_s), "unit": "clouds/s",
                                  "h2d_bytes_per_step": h2d32,
                                  "note": "same loop, index tables uploaded in the native int32 format"}},
-        "gpu_launches": launches, "clocks": clocks, "lattice_build": lattice, "correlation": corr, "model_forward": model_fwd,
+        "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+        "clocks": clocks, "lattice_build": lattice, "correlation": corr, "model_forward": model_fwd,
         "train_step": train,
     }
     print(json.dumps(line))
@@ -507,22 +596,25 @@ def model_leg(dev):
     pc1, pc2 = frustum_pair(N_POINTS, 7)
     a, b = torch.from_numpy(pc1.T.copy()).to(dev), torch.from_numpy(pc2.T.copy()).to(dev)
 
+    from hplflownet_b200 import ops
+
     def run(build):
         with torch.no_grad():
             gd = collate_batch1(gen.build(a, b)) if build else run.gd
             return model(a[None], b[None], gd)
     run.gd = collate_batch1(gen.build(a, b))
     out = {}
-    for name, build in (("forward_ms", False), ("build_plus_forward_ms", True)):
-        for _ in range(3):
-            run(build)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        reps = 8
-        for _ in range(reps):
-            y = run(build)
-        torch.cuda.synchronize()
-        out[name] = 1e3 * (time.perf_counter() - t0) / reps
+    with ops.weight_cache_scope():                           # evaluation: the weights are constant across calls
+        for name, build in (("forward_ms", False), ("build_plus_forward_ms", True)):
+            for _ in range(3):
+                run(build)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            reps = 8
+            for _ in range(reps):
+                y = run(build)
+            torch.cuda.synchronize()
+            out[name] = 1e3 * (time.perf_counter() - t0) / reps
     out.update({"workload": "HPLFlowNet forward, 8192+8192-pt pair, 7 scales, evaluate mode, random weights",
                 "pairs_per_s": 1e3 / out["build_plus_forward_ms"], "output_finite": bool(torch.isfinite(y).all()),
                 "note": "reference CPU forward: 13.8 s/pair + 4.1-4.9 s lattice build (SURVEY §6, 8 vCPU)"})

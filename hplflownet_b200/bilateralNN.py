@@ -82,7 +82,7 @@ def _plan_for_first_layer(nbr2, c_in, c_out0):
         return None
     from . import plans
     plan = plans.plan_for(nbr2)
-    return plan if plan.usable else None
+    return plan if (plan is not None and plan.usable) else None
 
 
 class _BCLFunction(torch.autograd.Function):

@@ -134,19 +134,53 @@ def build(nbr2, n_in_rows=None, order="spatial"):
     return TilePlan(buf, h, n_in, f, tuple(s), order, sweeps)
 
 
-def plan_for(nbr2):
-    """Cached plan of a same-lattice table (keyed by the tensor's storage / shape / dtype / version)."""
-    key = (nbr2.data_ptr(), tuple(nbr2.shape), nbr2.dtype, nbr2.device)
-    ent = _cache.get(key)
-    if ent is not None and ent[0]() is not None and ent[1] == nbr2._version:
-        return ent[2]
-    plan = build(nbr2)
+# Planning a table costs a coordinate reconstruction (tens of relaxation sweeps), a radix sort and a host read of the
+# statistics -- milliseconds, repaid over many kernel launches on a lattice that stays resident (a cached dataset, the
+# forward / data-gradient / weight-gradient of every layer and step that use it), but not on a table that is seen once
+# (a DataLoader that ships fresh tables every step).  So a table is planned when it is used for the SECOND time;
+# ``PLAN_ON_FIRST_USE`` (or an explicit ``plans.prepare(blur_neighbors)``) plans immediately.
+PLAN_ON_FIRST_USE = False
+
+
+def _key(nbr2):
+    return (nbr2.data_ptr(), tuple(nbr2.shape), nbr2.dtype, nbr2.device)
+
+
+def _remember(nbr2, key, plan):
     base = nbr2._base if nbr2._base is not None else nbr2
     try:
         ref = weakref.ref(base, lambda _r, k=key: _cache.pop(k, None))
     except TypeError:
-        return plan
+        return
     _cache[key] = (ref, nbr2._version, plan)
+
+
+def plan_for(nbr2):
+    """Cached plan of a same-lattice table (keyed by the tensor's storage / shape / dtype / version), or None while the
+    table has been seen only once (see PLAN_ON_FIRST_USE)."""
+    key = _key(nbr2)
+    ent = _cache.get(key)
+    fresh = ent is None or ent[0]() is None or ent[1] != nbr2._version
+    if not fresh and ent[2] is not None:
+        return ent[2]
+    if fresh and not PLAN_ON_FIRST_USE:
+        _remember(nbr2, key, None)
+        return None
+    plan = build(nbr2)
+    _remember(nbr2, key, plan)
+    return plan
+
+
+def prepare(blur_neighbors):
+    """Plan a table now (accepts the module-level (1, F, H) tensor or its (F, H) view) and return the plan."""
+    nbr2 = blur_neighbors[0] if blur_neighbors.dim() == 3 else blur_neighbors
+    nbr2 = nbr2.contiguous()
+    key = _key(nbr2)
+    ent = _cache.get(key)
+    if ent is not None and ent[0]() is not None and ent[1] == nbr2._version and ent[2] is not None:
+        return ent[2]
+    plan = build(nbr2)
+    _remember(nbr2, key, plan)
     return plan
 
 

@@ -24,3 +24,17 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _plan_tables_on_first_use(request):
+    """The parity tests call every module once per table; plan on first use so that engine 5 (tile plans) is what they
+    exercise wherever it applies.  (Production default: a table is planned when it is used for the second time.)"""
+    if "gpu" not in request.keywords:
+        yield
+        return
+    from hplflownet_b200 import plans
+    old = plans.PLAN_ON_FIRST_USE
+    plans.PLAN_ON_FIRST_USE = True
+    yield
+    plans.PLAN_ON_FIRST_USE = old

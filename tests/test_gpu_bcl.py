@@ -234,3 +234,42 @@ def test_weight_image_cache_follows_parameter_updates():
         assert_close(y4, y5, "no caching outside a scope")
     finally:
         ops.WEIGHT_CACHE = True
+
+
+def test_engine5_module_matches_engine2_and_plans_on_second_use(monkeypatch):
+    """Whole layer forward + backward on engine 5 (tile plan: forward, mirrored-tap data gradient, weight gradient) against
+    engine 2, and the production planning policy: a table is planned when it is seen for the second time."""
+    from hplflownet_b200 import ops, plans
+    d = _lattice(4096, 13, 1.0)
+    torch.manual_seed(2)
+    mod = hpl.BilateralConvFlex(3, 1, 64, [64, 32], "cuda", use_bias=True, use_leaky=True, use_norm=True,
+                                do_splat=True, do_slice=True, last_relu=False, chunk_size=-1).to(DEV)
+    feat = torch.randn(1, 64, 4096, device=DEV)
+    bary, off, nbr = d["pc1_barycentric"].to(DEV), d["pc1_lattice_offset"].to(DEV), d["pc1_blur_neighbors"].to(DEV)
+    gy = torch.randn(1, 32, 4096, device=DEV)
+
+    def run():
+        for p in mod.parameters():
+            p.grad = None
+        f = feat.clone().requires_grad_(True)
+        y = mod(f, bary, off, nbr, bary, off)
+        y.backward(gy)
+        return [y.detach().clone(), f.grad.clone()] + [p.grad.clone() for p in mod.parameters()]
+
+    monkeypatch.setattr(plans, "PLAN_ON_FIRST_USE", False)
+    plans.clear()
+    ops.PROFILE_GEMM = []
+    try:
+        first = run()                                    # first sighting of the table: engine 2
+        n_first = len(plans._cache)
+        assert n_first == 1 and next(iter(plans._cache.values()))[2] is None
+        second = run()                                   # second sighting: planned, engine 5
+        plan = next(iter(plans._cache.values()))[2]
+        assert plan is not None and plan.usable and plan.symmetric
+    finally:
+        ops.PROFILE_GEMM = None
+    for a, b in zip(second, first):
+        assert_close(a, b, "engine 5 vs engine 2")
+    monkeypatch.setattr(ops, "DEFAULT_PRECISION", 2)
+    for a, b in zip(run(), first):
+        assert_close(a, b, "engine 2 again")

@@ -46,6 +46,7 @@ constexpr uint32_t kB_LBO = 128 * 16;            // weight tile: 128 N rows ([W_
 constexpr int kBTap = 4 * kB_LBO;                // 8192
 constexpr int kBStage = 2 * kBTap;
 constexpr int kStages = 2;
+constexpr int kC5Slots = 4;                      // forward kernel: ring of one-tap stages
 constexpr int kIdxBuf = kTaps * TM * 2;          // 4096 B of uint16 slots
 constexpr int kCopyWarps = 8, kCopyThreads = kCopyWarps * 32;      // weight-gradient kernel: one copy group
 constexpr int kMmaWarp = 8, kWWarp = 9;
@@ -53,10 +54,12 @@ constexpr int kThreads = 14 * 32;
 // forward kernel: TWO copy groups of 8 warps, group g fills ring slot g (alternate stages), so one group's fixed latencies
 // (barrier wake-up, proxy fence) overlap the other group's shared-memory traffic
 constexpr int kC5CopyWarps = 16, kC5CopyThreads = kC5CopyWarps * 32;
-constexpr int kC5MmaWarp = 16, kC5WWarp = 17;                       // warps 18-21: epilogue
-constexpr int kC5Threads = 22 * 32;
+constexpr int kC5GroupWarps = kC5CopyWarps / 4;                     // four copy groups of four warps: group g fills ring slot g
+constexpr int kC5MmaWarp = 16, kC5LoadWarp = 18, kC5LoadWarps = 2;  // warps 16, 17: MMA issuers; 18, 19: row loaders; 20-23: epilogue
+constexpr int kC5LoadThreads = kC5LoadWarps * 32;
+constexpr int kC5Threads = 24 * 32;
 constexpr int kC5UIters = (kUmax * 8 + kC5CopyThreads - 1) / kC5CopyThreads;   // 8 row-chunk copies per thread and phase
-constexpr int kSmem = 2 * kUBuf + kStages * (kAStage + kBStage) + 2 * kIdxBuf + 1024;
+constexpr int kSmem = 2 * kUBuf + kC5Slots * (kATap + kBTap) + 2 * kIdxBuf + 1024;
 constexpr int kUIters = (kUmax * 8 + kCopyThreads - 1) / kCopyThreads;      // 15 row-chunk copies per thread and phase
 constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
 static_assert(kSmem <= 232448, "shared memory budget");
@@ -213,38 +216,46 @@ struct Conv5Args {
 };
 
 // F = taps processed (15: HPLFlowNet's r = 1 neighbourhood; 16: any other count, padded with zero taps)
+//
+// Pipeline.  A stage is ONE tap of one phase (A: 16.1 KB hi | lo planes, W: 8 KB), ring of kC5Slots = 4.  The stages of a
+// CTA are numbered G = 0, 1, 2, ... across phases and tiles (phase = G / F, tap = G % F, slot = G % 4); copy group g
+// (8 warps) fills the stages with G % 2 == g, i.e. it owns slots g and g + 2 and always has a second stage to work on
+// while the tensor core drains the first.  Measured on the previous structure (two-tap stages, ring of 2): a slot's
+// copy -> MMA -> copy chain carries ~1750 cycles of hand-over latency per round trip, so per-stage time was
+// latency + copy + MMA, not their maximum; four slots in flight hide it.
 template <int F>
 __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2 * kStages + 2 + 4];
+    __shared__ __align__(8) uint64_t bars[2 * kC5Slots + 4 + 4];
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t u_base = smem_base;                                   // 2 x kUBuf
-    const uint32_t a_base = u_base + 2 * kUBuf;                          // kStages x kAStage
-    const uint32_t b_base = a_base + kStages * kAStage;                  // kStages x kBStage
-    const uint32_t idx_base = b_base + kStages * kBStage;                // 2 x kIdxBuf
+    const uint32_t a_base = u_base + 2 * kUBuf;                          // kC5Slots x kATap
+    const uint32_t b_base = a_base + kC5Slots * kATap;                   // kC5Slots x kBTap
+    const uint32_t idx_base = b_base + kC5Slots * kBTap;                 // 2 x kIdxBuf
     const uint32_t bar0 = smem_u32(bars);
-    const uint32_t full = bar0, empty = full + 8 * kStages, ufull = empty + 8 * kStages;
-    const uint32_t acc_full = ufull + 16, acc_empty = acc_full + 16;
+    const uint32_t full = bar0, empty = full + 8 * kC5Slots, ufull = empty + 8 * kC5Slots, ufree = ufull + 16;
+    const uint32_t acc_full = ufree + 16, acc_empty = acc_full + 16;
 
     const int per = (p.n_tiles + gridDim.x - 1) / gridDim.x;
     const int t_begin = blockIdx.x * per;
     const int t_end = min(p.n_tiles, t_begin + per);
     const int n_my = max(0, t_end - t_begin);
     const int CB = p.cb_count;
-    constexpr int NP = (F + 1) / 2;                                      // stages per phase (two taps each)
-    static_assert(NP % 2 == 0 && kStages == 2, "stage s of a phase uses ring slot s & 1");
-    const int acc_cols = p.n_main * 128;                                 // TMEM columns of one accumulator set
+    const int n_phases = n_my * CB;
+    const int n_stages = n_phases * F;
+    const int acc_cols = 2 * p.n_main * 128;                             // TMEM columns of one tile: two issuers x n_main x [main | cross]
     const int acc_stages = 2 * acc_cols <= 512 ? 2 : 1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&bars[s], kCopyWarps + 1); mbar_init(&bars[kStages + s], 1); }
+        for (int s = 0; s < kC5Slots; ++s) { mbar_init(&bars[s], kC5GroupWarps + 1); mbar_init(&bars[kC5Slots + s], 1); }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&bars[2 * kStages + s], kC5CopyThreads);
-            mbar_init(&bars[2 * kStages + 2 + s], 1);
-            mbar_init(&bars[2 * kStages + 4 + s], 4);
+            mbar_init(&bars[2 * kC5Slots + s], kC5LoadThreads);          // ufull: the phase's rows have landed
+            mbar_init(&bars[2 * kC5Slots + 2 + s], kC5CopyWarps);        // ufree: every copy warp is done reading the buffer
+            mbar_init(&bars[2 * kC5Slots + 4 + s], 2);                   // acc_full: both MMA issuers have committed the tile
+            mbar_init(&bars[2 * kC5Slots + 6 + s], 4);
         }
         fence_mbar_init();
     }
@@ -262,173 +273,158 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
     if (warp < kC5CopyWarps) {
         // ------------------------------------------------------------------ copy warps
         // Their instruction stream paces the kernel (a first version with run-time tap / modulo tests ran ~500 dependent
-        // instructions per warp and stage: 2600 cycles per stage with everything else switched off), so everything is a
-        // compile-time schedule over per-thread constants: per stage 8 slot loads, 8 LDS.128, 8 STS.128 per thread.
+        // instructions per warp and stage), so addresses are per-thread constants plus a few adds: per stage 4 slot loads,
+        // 4 LDS.128, 4 STS.128 per thread; the staged rows are read BEFORE the wait for the stage buffer.
         const int tid = threadIdx.x;
-        const int grp = tid >> 8;                                        // copy group = ring slot it fills
-        const int gt = tid & 255;
+        const int grp = tid >> 7;                                        // copy group = ring slot it fills (stages G % 4 == grp)
+        const int gt = tid & 127;
         const int c8 = gt & 7;                                           // 16-byte chunk of a 128-byte line
-        const int rg = gt >> 3;                                          // 0..31: row within a group of 32
-        const long long row_bytes = (long long)CB * kURow;
-        const int n_phases = n_my * CB;
+        const int rg = gt >> 3;                                          // 0..15: row within a group of 16
         const uint32_t src_off = c8 * 16;
-        const uint32_t idx_off = rg * 2;                                 // + (tap * 128 + q * 32) * 2
-        // A-stage position of (row = q * 32 + rg, chunk c8): + tap_l * kATap + q * 512
-        const uint32_t abd = a_base + grp * kAStage + (c8 >> 2) * kAPlane + (c8 & 3) * kA_LBO + (rg >> 3) * 128 + (rg & 7) * 16;
-        const uint8_t* in_thread = p.in16 + src_off;
+        const uint32_t idx_off = rg * 2;                                 // + (tap * 128 + i * 16) * 2
+        // A position of (row = i * 16 + rg, chunk c8): + i * 256
+        const uint32_t dst_off = (c8 >> 2) * kAPlane + (c8 & 3) * kA_LBO + (rg >> 3) * 128 + (rg & 7) * 16;
+        const uint32_t abd = a_base + grp * kATap + dst_off;
         const uint32_t full_g = full + 8 * grp, empty_g = empty + 8 * grp;
 
-        // U rows are loaded by all 512 threads: thread -> rows (tid >> 3) + i * 64
-        int urow[kC5UIters];
-        auto fetch_rows = [&](int k) {                                   // row ids of tile k (0-based in this CTA's range)
-            const int t = t_begin + k;
-            const int n = __ldg(p.n_uniq + t);
-            const int* up = p.uniq + (long long)t * kUmax + (tid >> 3);
-#pragma unroll
-            for (int i = 0; i < kC5UIters; ++i)
-                urow[i] = (tid >> 3) + i * (kC5CopyThreads / 8) < min(n, kUmax) ? __ldg(up + i * (kC5CopyThreads / 8)) : -1;
-        };
-        auto load_idx_block = [&](int k) {                               // the tile's index block: 256 chunks of 16 B
-            if (tid < 256)
-                cp_async16(idx_base + (k & 1) * kIdxBuf + tid * 16,
-                           reinterpret_cast<const uint8_t*>(p.local) + ((long long)(t_begin + k) * (kTaps * TM)) * 2 + tid * 16);
-        };
-        // rows i0 .. i0+3 of this thread's list for channel block cb into U buffer `ub`
-        auto load_rows = [&](uint32_t ub, int cb, int i0) {
-            const uint8_t* src = in_thread + cb * kURow;
-            const uint32_t dst = ub + (tid >> 3) * kURow + src_off;
-#pragma unroll
-            for (int i = i0; i < i0 + 4; ++i)
-                if (i < kC5UIters && urow[i] >= 0 && !(p.dbg & 8))
-                    cp_async16(dst + i * (kC5CopyThreads / 8) * kURow, src + (long long)urow[i] * row_bytes);
-        };
-
-        if (n_phases > 0) {
-            fetch_rows(0);
-            load_idx_block(0);
-#pragma unroll
-            for (int i0 = 0; i0 < kC5UIters; i0 += 4) load_rows(u_base, 0, i0);
-            cp_async_arrive_noinc(ufull);
-        }
-        uint32_t phase_bit = 0;                                          // of this group's ring slot
-        int k = 0, cb = 0;
-        for (int ph = 0; ph < n_phases; ++ph) {
-            const bool has_next = ph + 1 < n_phases;
-            const bool next_new_tile = cb == CB - 1;
-            const int ncb = next_new_tile ? 0 : cb + 1;
-            if (has_next && next_new_tile) fetch_rows(k + 1);            // (consumed two stages later)
-            wait_bar(ufull + 8 * (ph & 1), (ph >> 1) & 1);
-            const uint32_t ub = u_base + (ph & 1) * kUBuf + src_off;
-            const uint32_t ubn = u_base + ((ph + 1) & 1) * kUBuf;
-            const uint32_t ibs = idx_base + (k & 1) * kIdxBuf + idx_off;
-#pragma unroll
-            for (int s2 = 0; s2 < NP / 2; ++s2) {
-                // this group's stage: s = 2 * s2 + grp (taps 2s, 2s + 1); s is uniform per warp, the tap tests fold for F = 16
-                const int s = 2 * s2 + grp;
-                const bool second = 2 * s + 1 < F;                        // the stage's second tap exists (F = 15: not in the last stage)
-                const bool tr = p.trace != nullptr && blockIdx.x == 0 && gt == 0 && ph * NP + s < 256;
-                long long* trp = p.trace + (ph * NP + s) * 8;
-                if (tr) trp[0] = clock64();
-                uint32_t slot[8];
-                uint4 v[8];
-                if (!(p.dbg & 1)) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (i < 4 || second) slot[i] = lds_u16(ibs + (2 * s + (i >> 2)) * (TM * 2) + (i & 3) * 64);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (i < 4 || second) v[i] = lds128(ub + slot[i] * kURow);
+        int ph = -1, k = 0, cb = 0;                                       // current phase and its (tile, channel block)
+        int next_ph_tap0 = 0;                                            // stage number where the next phase starts
+        uint32_t ub = 0, ibs = 0;
+        for (int G = grp; G < n_stages; G += kC5Slots) {
+            if (G >= next_ph_tap0) {                                     // this group's first stage of a new phase
+                if (ph >= 0) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_a(ufree + 8 * (ph & 1));  // this warp is done reading the previous phase's rows
+                    if (++cb == CB) { cb = 0; ++k; }
                 }
-                if (lane == 0) wait_bar(empty_g, phase_bit ^ 1);
-                __syncwarp();
-                if (tr) trp[1] = clock64();
-                if (!(p.dbg & 1)) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (i < 4 || second) sts128(abd + (i >> 2) * kATap + (i & 3) * 512, v[i].x, v[i].y, v[i].z, v[i].w);
-                }
-                if (tr) trp[2] = clock64();
-                // the next phase's rows: issued during this group's first two stages, so they have the rest of the phase to land
-                if (has_next && s2 < 2) {
-                    if (s2 == 0 && next_new_tile) load_idx_block(k + 1);
-                    load_rows(ubn, ncb, 4 * s2);
-                    if (s2 == 1) cp_async_arrive_noinc(ufull + 8 * ((ph + 1) & 1));
-                }
-                if (tr) trp[3] = clock64();
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_a(full_g);
-                if (tr) trp[4] = clock64();
-                phase_bit ^= 1;
+                ++ph;
+                next_ph_tap0 += F;
+                wait_bar(ufull + 8 * (ph & 1), (ph >> 1) & 1);
+                ub = u_base + (ph & 1) * kUBuf + src_off;
+                ibs = idx_base + (k & 1) * kIdxBuf + idx_off;
             }
-            // every copy thread has finished reading this phase's U buffer (and, at the end of a tile, its index block)
-            asm volatile("bar.sync 1, %0;" ::"n"(kC5CopyThreads) : "memory");
-            if (++cb == CB) { cb = 0; ++k; }
-        }
-    } else if (warp == kC5WWarp) {
-        // ------------------------------------------------------------------ weight stream
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase_bit = 0;
-            for (int k = 0; k < n_my; ++k)
-                for (int cb = 0; cb < CB; ++cb) {
-                    const uint8_t* src = p.w_image + (long long)cb * kTaps * kBTap;
-                    for (int s = 0; s < NP; ++s) {
-                        wait_bar(empty + 8 * stage, phase_bit ^ 1);
-                        if (p.dbg & 4) {
-                            mbar_arrive_a(full + 8 * stage);
-                        } else {
-                            mbar_arrive_expect_tx_a(full + 8 * stage, kBStage);
-                            bulk_load_a(b_base + stage * kBStage, src + (long long)s * kBStage, kBStage, full + 8 * stage);
-                        }
-                        if (++stage == kStages) { stage = 0; phase_bit ^= 1; }
+            const int tap = G - (next_ph_tap0 - F);
+            const bool tr = p.trace != nullptr && blockIdx.x == 0 && gt == 0 && G < 256;
+            long long* trp = p.trace + G * 8;
+            if (tr) trp[0] = clock64();
+            uint32_t slot[8];
+            uint4 v[8];
+            if (!(p.dbg & 1)) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) slot[i] = lds_u16(ibs + tap * (TM * 2) + i * 32);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = lds128(ub + slot[i] * kURow);
+            }
+            if (lane == 0) {
+                wait_bar(empty_g, ((G >> 2) & 1) ^ 1);
+                // the stage's weight tile (8 KB, one bulk copy) is requested by the group itself as soon as the slot is free: a
+                // dedicated weight-stream thread walking ALL stages paid a barrier wake-up (~300-600 cycles) per stage in
+                // series and capped the whole pipeline at that rate
+                if ((gt >> 5) == 0) {
+                    if (p.dbg & 4) {
+                        mbar_arrive_a(full_g);
+                    } else {
+                        mbar_arrive_expect_tx_a(full_g, kBTap);
+                        bulk_load_a(b_base + grp * kBTap, p.w_image + ((long long)cb * kTaps + tap) * kBTap, kBTap, full_g);
                     }
                 }
+            }
+            __syncwarp();
+            if (tr) trp[1] = clock64();
+            if (!(p.dbg & 1)) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sts128(abd + i * 256, v[i].x, v[i].y, v[i].z, v[i].w);
+            }
+            if (tr) trp[2] = clock64();
+            if (tr) trp[3] = clock64();
+            if (!(p.dbg & 32)) fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(full_g);
+            if (tr) trp[4] = clock64();
         }
-    } else if (warp == kC5MmaWarp) {
-        // ------------------------------------------------------------------ MMA issuer
+    } else if (warp >= kC5LoadWarp && warp < kC5LoadWarp + kC5LoadWarps) {
+        // ------------------------------------------------------------------ row loaders
+        // Stage the distinct rows (and the index block) of the phases, one phase ahead of the copy groups.  They are separate
+        // warps because fence.proxy.async -- which every copy thread executes once per stage -- waits for the thread's
+        // outstanding cp.async as well: with the loads issued by the copy threads themselves, half of their stages
+        // stalled ~1500 cycles (an L2 round trip) in that fence.
+        const int lt = threadIdx.x - kC5LoadWarp * 32;                    // 0 .. 63
+        const int c8 = lt & 7, r0 = lt >> 3;                              // chunk of the line; rows r0, r0 + 8, ...
+        const long long row_bytes = (long long)CB * kURow;
+        int k = 0, cb = 0;
+        for (int ph = 0; ph < n_phases; ++ph) {
+            // the buffer held phase ph - 2: every copy warp has left it
+            if (ph >= 2) wait_bar(ufree + 8 * (ph & 1), ((ph - 2) >> 1) & 1);
+            const int t = t_begin + k;
+            const uint32_t ub = u_base + (ph & 1) * kUBuf + c8 * 16;
+            if (cb == 0) {                                               // the tile's index block: 256 chunks of 16 B
+#pragma unroll
+                for (int i = 0; i < 256 / kC5LoadThreads; ++i)
+                    cp_async16(idx_base + (k & 1) * kIdxBuf + (lt + i * kC5LoadThreads) * 16,
+                               reinterpret_cast<const uint8_t*>(p.local) + ((long long)t * (kTaps * TM)) * 2 + (lt + i * kC5LoadThreads) * 16);
+            }
+            const int n = min(__ldg(p.n_uniq + t), kUmax);
+            const int* up = p.uniq + (long long)t * kUmax;
+            const uint8_t* src = p.in16 + cb * kURow + c8 * 16;
+            if (!(p.dbg & 8)) {
+                for (int j0 = r0; j0 < n; j0 += 8 * 8) {                 // 8 rows in flight per thread
+                    int rows[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) rows[i] = j0 + 8 * i < n ? __ldg(up + j0 + 8 * i) : -1;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (rows[i] >= 0) cp_async16(ub + (j0 + 8 * i) * kURow, src + (long long)rows[i] * row_bytes);
+                }
+            }
+            cp_async_arrive_noinc(ufull + 8 * (ph & 1));
+            if (++cb == CB) { cb = 0; ++k; }
+        }
+    } else if (warp == kC5MmaWarp || warp == kC5MmaWarp + 1) {
+        // ------------------------------------------------------------------ MMA issuers (one thread each)
+        // A lone thread needs ~80 cycles per tcgen05.mma (uniform-datapath descriptor arithmetic, R2UR, the ELECT wrapper)
+        // plus ~400 for the barrier wait and the commit of a stage -- more than the 96 cycles the tensor core needs for a K
+        // step, so ONE issuer caps the tensor pipe near 20 %.  Two issuers take alternate stages (issuer i: G % 2 == i,
+        // i.e. ring slots i and i + 2); each accumulates into its own TMEM columns (the order of tcgen05.mma between
+        // threads is not defined, and separate accumulators keep the result deterministic); the epilogue adds them.
         if (lane == 0) {
+            const int me = warp - kC5MmaWarp;
             constexpr uint32_t kIdescMain = instr_desc(0, TM, 128, 0, 0);
             constexpr uint32_t kIdescLo = instr_desc(0, TM, 64, 0, 0);
             constexpr uint64_t kDescA = (uint64_t)((kA_LBO >> 4) & 0x3fff) << 16 | (uint64_t)(128 >> 4) << 32 | (uint64_t)1 << 46;
             constexpr uint64_t kDescB = (uint64_t)((kB_LBO >> 4) & 0x3fff) << 16 | (uint64_t)(128 >> 4) << 32 | (uint64_t)1 << 46;
-            int stage = 0, acc = 0;
-            uint32_t phase_bit = 0, pacc = 0;
+            const int per_tile = CB * F;
+            int acc = 0;
+            uint32_t pacc = 0;
             for (int k = 0; k < n_my; ++k) {
                 wait_bar(acc_empty + 8 * acc, pacc ^ 1);
                 fence_after();
-                const uint32_t d0 = tmem_d + (uint32_t)(acc * acc_cols);
-                int g = 0, g_num = 0, pg = -1;                           // main accumulator of the current K step
-                for (int cb = 0; cb < CB; ++cb)
+                const uint32_t d0 = tmem_d + (uint32_t)(acc * acc_cols + me * p.n_main * 128);
+                const int G0 = k * per_tile;
+                int pg = -1;
+                for (int s = (G0 + me) & 1 ? 1 : 0; s < per_tile; s += 2) {   // stages of this tile with (G0 + s) % 2 == me
+                    const int G = G0 + s;
+                    const int slot_i = G & (kC5Slots - 1);
+                    const bool tr = p.trace != nullptr && blockIdx.x == 0 && G < 256;
+                    if (tr) p.trace[G * 8 + 5] = clock64();
+                    wait_bar(full + 8 * slot_i, (G >> 2) & 1);
+                    fence_after();
+                    if (tr) p.trace[G * 8 + 6] = clock64();
+                    const uint32_t a16 = (a_base + slot_i * kATap) >> 4, b16 = (b_base + slot_i * kBTap) >> 4;
+                    if (!(p.dbg & 2)) {
 #pragma unroll
-                    for (int s = 0; s < NP; ++s) {
-                        const int sidx = (k * CB + cb) * NP + s;
-                        const bool tr = p.trace != nullptr && blockIdx.x == 0 && sidx < 256;
-                        if (tr) p.trace[sidx * 8 + 5] = clock64();
-                        wait_bar(full + 8 * stage, phase_bit);
-                        fence_after();
-                        if (tr) p.trace[sidx * 8 + 6] = clock64();
-                        const uint32_t a16 = (a_base + stage * kAStage) >> 4, b16 = (b_base + stage * kBStage) >> 4;
-#pragma unroll
-                        for (int tap_l = 0; tap_l < 2; ++tap_l) {
-                            if (2 * s + tap_l < F && !(p.dbg & 2)) {
-#pragma unroll
-                                for (int j = 0; j < 2; ++j) {
-                                    const uint32_t ah = a16 + ((tap_l * kATap + j * 2 * kA_LBO) >> 4);
-                                    const uint32_t bb = b16 + ((tap_l * kBTap + j * 2 * kB_LBO) >> 4);
-                                    const uint32_t dg = d0 + (uint32_t)(g * 128);
-                                    umma_f16(dg, kDescA | ah, kDescB | bb, kIdescMain, g == pg);                   // x_hi . [W_hi | W_lo]
-                                    umma_f16(dg + 64, kDescA | (ah + (kAPlane >> 4)), kDescB | bb, kIdescLo, 1);   // x_lo . W_hi
-                                    pg = g;
-                                    g_num += p.n_main;
-                                    if (g_num >= p.steps_total) { g_num -= p.steps_total; ++g; }
-                                }
-                            }
+                        for (int j = 0; j < 2; ++j) {
+                            const int g = p.n_main == 1 ? 0 : ((2 * s + j) * p.n_main) / p.steps_total;   // main accumulator of this K step
+                            const uint32_t ah = a16 + ((j * 2 * kA_LBO) >> 4);
+                            const uint32_t bb = b16 + ((j * 2 * kB_LBO) >> 4);
+                            const uint32_t dg = d0 + (uint32_t)(g * 128);
+                            umma_f16(dg, kDescA | ah, kDescB | bb, kIdescMain, g == pg);                   // x_hi . [W_hi | W_lo]
+                            umma_f16(dg + 64, kDescA | (ah + (kAPlane >> 4)), kDescB | bb, kIdescLo, 1);   // x_lo . W_hi
+                            pg = g;
                         }
-                        umma_commit_a(empty + 8 * stage);
-                        if (tr) p.trace[sidx * 8 + 7] = clock64();
-                        if (++stage == kStages) { stage = 0; phase_bit ^= 1; }
                     }
+                    umma_commit_a(empty + 8 * slot_i);
+                    if (tr) p.trace[G * 8 + 7] = clock64();
+                }
                 umma_commit_a(acc_full + 8 * acc);
                 if (++acc == acc_stages) { acc = 0; pacc ^= 1; }
             }
@@ -455,17 +451,19 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
                 if (c0 >= p.c_out) break;
                 float sum[16];
                 uint32_t v[16];
-                tmem_ld16(taddr + 64 + c0, v);                               // cross terms of accumulator 0
+                // accumulator sets of the tile: (issuer, main accumulator) -> 128 columns [main | cross]
+                const int n_sets = 2 * p.n_main;
+                tmem_ld16(taddr + 64 + c0, v);                               // cross terms
 #pragma unroll
                 for (int j = 0; j < 16; ++j) sum[j] = __uint_as_float(v[j]);
-                for (int g = 1; g < p.n_main; ++g) {
+                for (int g = 1; g < n_sets; ++g) {
                     tmem_ld16(taddr + g * 128 + 64 + c0, v);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) sum[j] += __uint_as_float(v[j]);
                 }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) sum[j] *= kLoInv;
-                for (int g = 0; g < p.n_main; ++g) {
+                for (int g = 0; g < n_sets; ++g) {
                     tmem_ld16(taddr + g * 128 + c0, v);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) sum[j] += __uint_as_float(v[j]);
@@ -871,7 +869,7 @@ int hpl_conv5(const void* x16, const void* plan, int64_t n_out_rows, int64_t fil
     a.n_tiles = (int)hpl_plan_tiles(n_out_rows);
     a.cb_count = cb; a.filter_size = (int)filter_size; a.c_out = (int)c_out; a.act = act;
     a.steps_total = (int)((filter_size == 15 ? 15 : 16) * cb * 2);
-    a.n_main = (a.steps_total + 159) / 160;
+    a.n_main = (a.steps_total + 319) / 320;                  // <= ~160 accumulate steps per accumulator, two issuers share the K steps
     { const char* e = getenv("HPL_CONV5_DBG"); a.dbg = e ? atoi(e) : 0; }
     a.trace = nullptr;
     { const char* e = getenv("HPL_CONV5_TRACE"); if (e) a.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0)); }

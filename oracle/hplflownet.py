@@ -20,7 +20,7 @@ def _conv1d_relu(x, w, b, leaky, act=True):
     y = F.conv1d(x, w, b)
     if not act:
         return y
-    return F.leaky_relu(y, OB.LEAKY_RATE) if leaky else F.relu(y)
+    return OB._act(y, leaky)
 
 
 def forward(state, pc1, pc2, gd, *, use_leaky=True, use_norm=True, use_bias=True):

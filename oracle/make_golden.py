@@ -182,6 +182,24 @@ def dump_model(T, name, *, n, seed, shallow=False):
     print(name, tuple(out.shape), float(out.abs().max()))
 
 
+def dump_state_layout(name):
+    """Full ``state_dict`` key -> [shape, dtype] list of the reference HPLFlowNet and HPLFlowNetShallow (the checkpoint
+    contract, main.py:122 loads with strict=True) as JSON."""
+    import json
+    sys.path.insert(0, REPO)
+    from tests._util import ModelArgs, ShallowArgs
+    from models.HPLFlowNet import HPLFlowNet
+    from models.HPLFlowNet_shallow import HPLFlowNetShallow
+    out = {}
+    for key, cls, args in (("HPLFlowNet", HPLFlowNet, ModelArgs()), ("HPLFlowNetShallow", HPLFlowNetShallow, ShallowArgs())):
+        args.DEVICE = "cpu"
+        sd = cls(args).state_dict()
+        out[key] = {k: [list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in sd.items()}
+    with open(os.path.join(GOLDEN, name), "w") as f:
+        json.dump(out, f, indent=0, sort_keys=True)
+    print(name, {k: len(v) for k, v in out.items()})
+
+
 def main():
     T, BCL, Corr = import_reference()
     sys.path.insert(0, REPO)
@@ -219,6 +237,7 @@ def main():
     # --- caller of the path: full HPLFlowNet forward (BASELINE configs[3] at reduced N) ---
     dump_model(T, "model_frustum256.npz", n=256, seed=3)
     dump_model(T, "model_shallow_frustum256.npz", n=256, seed=4, shallow=True)
+    dump_state_layout("state_dict_layout.json")
 
     # --- value path: BilateralCorrelationFlex ---
     dump_corr(T, Corr, "corr_prev8.npz", n=160, seed=5, c=8, corr_out=[8, 8], out_ch=[16, 16],

@@ -75,19 +75,40 @@ def oracle_state(module):
             for k, v in module.state_dict().items()}
 
 
-def assert_close_grad(got, ref, what=""):
+class kink_ledger:
+    """Context manager around an ORACLE evaluation: counts the activation units whose pre-activation lies within
+    ``oracle.bcl.KINK_TOL`` (relative to the layer's largest) of zero.  ``ledger.ambiguous`` is that count."""
+
+    def __enter__(self):
+        from oracle import bcl as OB
+        self._ob = OB
+        self._old = OB.KINK_LOG
+        OB.KINK_LOG = []
+        return self
+
+    def __exit__(self, *a):
+        log = self._ob.KINK_LOG
+        self._ob.KINK_LOG = self._old
+        self.units = sum(n for n, _ in log)
+        self.ambiguous = sum(k for _, k in log)
+        self.layers = len(log)
+
+
+FALLBACKS = []        # (test id / what, e_max, e_l2, ambiguous units) of every gradient tensor that needed the loose bound
+
+
+def assert_close_grad(got, ref, what="", ledger=None):
     """Gradient parity with activation-kink tolerance.
 
-    Forward values are continuous in their inputs and are always held to REL_TOL (max norm).
-    Gradients pass through (Leaky)ReLU derivatives, which are discontinuous at 0: among the
-    ~10^6 pre-activations of a layer a few lie within fp32 rounding of zero, and ANY two fp32
-    evaluations with different summation order (this path vs the reference on another BLAS, or
-    the reference vs itself in float64 -- measured 2e-3..7e-3 on exactly the tensors upstream of
-    one flipped unit) pick different slopes there.  Such a flip perturbs the affected gradient
-    entries by ~1/sqrt(#terms) relative.  So: strict REL_TOL first; otherwise the mismatch must
-    look like isolated flips -- small in max norm (<= 3e-2) and in relative L2 (<= 3e-3) -- never
-    like an indexing or scaling bug (O(1) errors).  The committed reference fixtures are held to
-    the strict REL_TOL for gradients as well.
+    Forward values are continuous in their inputs and are always held to REL_TOL (max norm).  Gradients pass through
+    (Leaky)ReLU derivatives, which are discontinuous at 0: a pre-activation within fp32 rounding of zero picks a different
+    slope under ANY change of summation order (this path vs the reference on another BLAS, or the reference vs itself in
+    float64), and one flipped unit perturbs the gradients upstream of it by ~1/sqrt(#terms) relative.  So: strict REL_TOL
+    first.  The loose bound -- isolated flips: max norm <= 3e-2, relative L2 <= 3e-3, never an indexing or scaling bug --
+    has to prove itself: with a ``ledger`` (``kink_ledger`` around the float64 oracle run) it is available ONLY when the
+    oracle saw at least one unit within 1e-5 of a kink; a tensor that fails REL_TOL with no such unit anywhere fails
+    the test.  Every use of the loose bound is recorded in ``FALLBACKS`` and listed in the pytest summary
+    (tests/conftest.py).  The committed reference fixtures are held to the strict REL_TOL for gradients as well.
     """
     g = torch.as_tensor(got).double().cpu()
     r = torch.as_tensor(ref).double().cpu()
@@ -99,6 +120,10 @@ def assert_close_grad(got, ref, what=""):
     if e_max <= REL_TOL:
         return
     e_l2 = ((g - r).norm() / r.norm().clamp_min(1e-30)).item()
+    amb = ledger.ambiguous if ledger is not None else None
+    assert amb is None or amb > 0, \
+        "%s: rel err max %.3e with NO activation unit near a kink in the oracle (%d units)" % (what, e_max, ledger.units)
+    FALLBACKS.append((os.environ.get("PYTEST_CURRENT_TEST", "").split(" ")[0] + " :: " + what, e_max, e_l2, amb))
     assert e_max <= 3e-2 and e_l2 <= 3e-3, "%s: rel err max %.3e, L2 %.3e" % (what, e_max, e_l2)
 
 

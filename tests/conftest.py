@@ -38,3 +38,15 @@ def _plan_tables_on_first_use(request):
     plans.PLAN_ON_FIRST_USE = True
     yield
     plans.PLAN_ON_FIRST_USE = old
+
+
+def pytest_terminal_summary(terminalreporter):
+    """Which gradient tensors needed the activation-kink bound of tests/_util.py:assert_close_grad, and why."""
+    try:
+        from tests._util import FALLBACKS
+    except Exception:
+        return
+    tr = terminalreporter
+    tr.write_line("gradient tensors checked with the activation-kink bound instead of 1e-5: %d" % len(FALLBACKS))
+    for what, e_max, e_l2, amb in FALLBACKS:
+        tr.write_line("  %s: max %.2e, L2 %.2e, oracle units near a kink: %s" % (what, e_max, e_l2, amb))

@@ -104,3 +104,21 @@ def test_model_state_dict_is_reference_layout():
         assert k in sd, k
     assert sd["bcn1_.blur_conv.0.composed_module.0.weight"].shape == (1024, 580, 15, 1)
     assert sd["corr2.corr_conv.0.composed_module.0.weight"].shape == (32, 192, 1, 15, 1)
+
+
+def test_full_state_dict_layout_matches_the_reference_models():
+    """Every key, shape and dtype of the reference HPLFlowNet / HPLFlowNetShallow ``state_dict`` (dumped from the
+    unmodified reference by oracle/make_golden.py:dump_state_layout; main.py:122 loads checkpoints with strict=True)."""
+    import json
+    import os
+    from hplflownet_b200.HPLFlowNet import HPLFlowNet
+    from hplflownet_b200.HPLFlowNet_shallow import HPLFlowNetShallow
+    from tests._util import GOLDEN, ModelArgs, ShallowArgs
+    want = json.load(open(os.path.join(GOLDEN, "state_dict_layout.json")))
+    for name, cls, args in (("HPLFlowNet", HPLFlowNet, ModelArgs()), ("HPLFlowNetShallow", HPLFlowNetShallow, ShallowArgs())):
+        sd = cls(args).state_dict()
+        got = {k: [list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in sd.items()}
+        assert list(got) == sorted(got, key=list(got).index)          # (dict order is insertion order)
+        assert set(got) == set(want[name]), (sorted(set(got) ^ set(want[name]))[:10])
+        for k, v in want[name].items():
+            assert got[k] == v, (name, k, got[k], v)

@@ -7,7 +7,7 @@ import hplflownet_b200 as hpl
 from hplflownet_b200.synthetic import frustum_pair
 from oracle import bcl as OB
 from oracle import lattice as OL
-from tests._util import assert_close, assert_close_grad, golden, golden_files, grads_from, oracle_state, state_from, t
+from tests._util import assert_close, assert_close_grad, golden, golden_files, grads_from, kink_ledger, oracle_state, state_from, t
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -58,7 +58,8 @@ def test_corr_matches_oracle(n, c, prev_dim, idx_dtype):
 
     # oracle evaluated in float64 (see tests/_util.py:oracle_state)
     r1, r2, rp = [x.double().requires_grad_(True) for x in (f1, f2, prev)]
-    y_ref = OB.corr_forward(state, r1, r2, rp, bary.double(), off, i1, i2, use_norm=True, use_leaky=True)
+    with kink_ledger() as ledger:
+        y_ref = OB.corr_forward(state, r1, r2, rp, bary.double(), off, i1, i2, use_norm=True, use_leaky=True)
     y_ref.backward(gy.double())
 
     g1, g2, gp = [x.to(DEV).requires_grad_(True) for x in (f1, f2, prev)]
@@ -67,8 +68,8 @@ def test_corr_matches_oracle(n, c, prev_dim, idx_dtype):
     y.backward(gy.to(DEV))
     assert y.shape == (1, 64, h1)
     assert_close(y, y_ref.detach(), "output")
-    assert_close_grad(g1.grad, r1.grad, "grad_feat1")
-    assert_close_grad(g2.grad, r2.grad, "grad_feat2")
-    assert_close_grad(gp.grad, rp.grad, "grad_prev")
+    assert_close_grad(g1.grad, r1.grad, "grad_feat1", ledger)
+    assert_close_grad(g2.grad, r2.grad, "grad_feat2", ledger)
+    assert_close_grad(gp.grad, rp.grad, "grad_prev", ledger)
     for k, p in mod.named_parameters():
-        assert_close_grad(p.grad, state[k].grad, "grad " + k)
+        assert_close_grad(p.grad, state[k].grad, "grad " + k, ledger)

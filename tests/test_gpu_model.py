@@ -64,7 +64,9 @@ def test_model_backward_matches_float64_oracle():
     gd_ref = [{k: (v.double() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in d.items()} for d in gd_ref]
     p1, p2 = [torch.from_numpy(np.ascontiguousarray(g[k].T))[None] for k in ("pc1", "pc2")]
     target = torch.from_numpy(np.ascontiguousarray((g["pc2"] - g["pc1"]).T))[None]
-    out_ref = OM.forward(state, p1.double(), p2.double(), gd_ref)
+    from tests._util import kink_ledger
+    with kink_ledger() as ledger:
+        out_ref = OM.forward(state, p1.double(), p2.double(), gd_ref)
     loss_ref = torch.norm(out_ref - target.double(), p=2, dim=1).mean()        # EPE3D loss, models/epe3d_loss.py:9
     loss_ref.backward()
 
@@ -79,7 +81,7 @@ def test_model_backward_matches_float64_oracle():
     for name, p in model.named_parameters():
         if p.grad is None:
             continue
-        assert_close_grad(p.grad, state[name].grad, "grad " + name)
+        assert_close_grad(p.grad, state[name].grad, "grad " + name, ledger)
         checked += 1
     assert checked >= 100
 
@@ -108,7 +110,9 @@ def test_shallow_model_forward_and_backward():
     gd_ref = [{k: (v.double() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in d.items()} for d in gd_ref]
     p1, p2 = [torch.from_numpy(np.ascontiguousarray(g[k].T))[None] for k in ("pc1", "pc2")]
     target = torch.from_numpy(np.ascontiguousarray((g["pc2"] - g["pc1"]).T))[None]
-    loss_ref = torch.norm(OM.forward_shallow(state, p1.double(), p2.double(), gd_ref) - target.double(), p=2, dim=1).mean()
+    from tests._util import kink_ledger
+    with kink_ledger() as ledger:
+        loss_ref = torch.norm(OM.forward_shallow(state, p1.double(), p2.double(), gd_ref) - target.double(), p=2, dim=1).mean()
     loss_ref.backward()
     model.train()
     loss = torch.norm(model(pc1[None], pc2[None], collate_batch1(gd)) - sf[None], p=2, dim=1).mean()
@@ -117,7 +121,7 @@ def test_shallow_model_forward_and_backward():
     checked = 0
     for name, p in model.named_parameters():
         if p.grad is not None:
-            assert_close_grad(p.grad, state[name].grad, "grad " + name)
+            assert_close_grad(p.grad, state[name].grad, "grad " + name, ledger)
             checked += 1
     assert checked >= 60
 
@@ -166,7 +170,9 @@ def test_model_backward_baseline_size_matches_float64_oracle():
     gd_ref = [{k: (v.double() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in d.items()} for d in gd_ref]
     p1, p2 = [torch.from_numpy(np.ascontiguousarray(p.T))[None].double() for p in (pc1, pc2)]
     target = torch.from_numpy(np.ascontiguousarray((pc2 - pc1).T))[None].double()
-    loss_ref = torch.norm(OM.forward(state, p1, p2, gd_ref) - target, p=2, dim=1).mean()
+    from tests._util import kink_ledger
+    with kink_ledger() as ledger:
+        loss_ref = torch.norm(OM.forward(state, p1, p2, gd_ref) - target, p=2, dim=1).mean()
     loss_ref.backward()
 
     model = model.cuda().train()
@@ -178,6 +184,6 @@ def test_model_backward_baseline_size_matches_float64_oracle():
     checked = 0
     for name, p in model.named_parameters():
         if p.grad is not None:
-            assert_close_grad(p.grad, state[name].grad, "grad " + name)
+            assert_close_grad(p.grad, state[name].grad, "grad " + name, ledger)
             checked += 1
     assert checked >= 100

@@ -105,6 +105,30 @@ __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity) {
     }
 }
 
+// polling wait for the two MMA-issuing threads (alone in their warps): test_wait returns at once, so the issuer reacts
+// within one poll instead of a suspend / wake-up round trip
+__device__ __forceinline__ void wait_bar_poll(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    unsigned long long t0 = 0;
+    for (uint32_t tries = 0; !done; ++tries) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done && (tries & 0xffff) == 0xffff) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) __trap();
+        }
+    }
+}
+
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -250,7 +274,7 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
     const int acc_stages = 2 * acc_cols <= 512 ? 2 : 1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kC5Slots; ++s) { mbar_init(&bars[s], kC5GroupWarps + 1); mbar_init(&bars[kC5Slots + s], 1); }
+        for (int s = 0; s < kC5Slots; ++s) { mbar_init(&bars[s], 1); mbar_init(&bars[kC5Slots + s], 1); }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&bars[2 * kC5Slots + s], kC5LoadThreads);          // ufull: the phase's rows have landed
             mbar_init(&bars[2 * kC5Slots + 2 + s], kC5CopyWarps);        // ufree: every copy warp is done reading the buffer
@@ -315,21 +339,16 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = lds128(ub + slot[i] * kURow);
             }
-            if (lane == 0) {
+            // One mbarrier wait and one arrival per GROUP and stage (named barriers inside the group): the SM's mbarrier
+            // unit serialises its operations (~40 cycles each, measured: an empty pipeline with one wait + one arrival per
+            // WARP ran at ~500 cycles per stage), so they are kept off the per-warp path.
+            if (gt == 0) {
                 wait_bar(empty_g, ((G >> 2) & 1) ^ 1);
-                // the stage's weight tile (8 KB, one bulk copy) is requested by the group itself as soon as the slot is free: a
-                // dedicated weight-stream thread walking ALL stages paid a barrier wake-up (~300-600 cycles) per stage in
-                // series and capped the whole pipeline at that rate
-                if ((gt >> 5) == 0) {
-                    if (p.dbg & 4) {
-                        mbar_arrive_a(full_g);
-                    } else {
-                        mbar_arrive_expect_tx_a(full_g, kBTap);
-                        bulk_load_a(b_base + grp * kBTap, p.w_image + ((long long)cb * kTaps + tap) * kBTap, kBTap, full_g);
-                    }
-                }
+                // the stage's weight tile (8 KB, one bulk copy) is requested by the group itself as soon as the slot is free
+                // (its complete_tx may land before the expect_tx below: the transaction count may go negative meanwhile)
+                if (!(p.dbg & 4)) bulk_load_a(b_base + grp * kBTap, p.w_image + ((long long)cb * kTaps + tap) * kBTap, kBTap, full_g);
             }
-            __syncwarp();
+            asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kC5GroupWarps * 32) : "memory");
             if (tr) trp[1] = clock64();
             if (!(p.dbg & 1)) {
 #pragma unroll
@@ -338,8 +357,11 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
             if (tr) trp[2] = clock64();
             if (tr) trp[3] = clock64();
             if (!(p.dbg & 32)) fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_a(full_g);
+            asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kC5GroupWarps * 32) : "memory");
+            if (gt == 0) {
+                if (p.dbg & 4) mbar_arrive_a(full_g);
+                else mbar_arrive_expect_tx_a(full_g, kBTap);
+            }
             if (tr) trp[4] = clock64();
         }
     } else if (warp >= kC5LoadWarp && warp < kC5LoadWarp + kC5LoadWarps) {

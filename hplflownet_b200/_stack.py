@@ -62,11 +62,46 @@ def forward(x, c_in, n_rows, layers, first_nbr=None, last_channel_major=False, f
     return xs, chans, out_cm, amaxs
 
 
+def _backward_single_layer5(dx, xs, chans, layer, first_nbr_t, need_input_grad, need_param_grad, amaxs, first5, dz_bound):
+    """A one-layer stack on engine 5 whose dz magnitude is bounded by the product of two device scalars (slice backward:
+    max|g| x max weight sum): ONE pass applies act', writes the operand image and the bias gradient and hands the
+    accumulator back to the zero pool; then the weight and data gradients run on the plan."""
+    w, b, act = layer
+    plan = first5.plan
+    x_amax, x16 = amaxs[0]
+    dgrad5 = need_input_grad and plan.symmetric and ops.conv5_supported(w.size(0), chans[1], chans[0])
+    keep_fp32 = need_input_grad and not dgrad5                     # engine 2 will gather fp32 rows
+    db = dx.new_zeros(chans[1]) if (need_param_grad and b is not None) else None
+    dz_amax = ops.amax_slots(dx.device, 1)
+    dz16 = ops.h16b_split_ex(dx, chans[1], dz_bound[0], y=xs[1] if act != ops.ACT_NONE else None, act=act,
+                             amax_b=dz_bound[1], amax_out=dz_amax, colsum=db, dispose=1 if keep_fp32 else 2)
+    grads = [None]
+    if need_param_grad:
+        grads[0] = (ops.wgrad5(x16, dz16, plan, chans[0], chans[1], x_amax, dz_amax), db)
+    out = None
+    if need_input_grad:
+        wd = w.transpose(1, 2)                                    # (F, Co, C) view
+        owner = getattr(w, "_hpl_owner", None)
+        if owner is not None:
+            ops.with_owner(wd, owner[0], "dgrad")
+        if dgrad5:
+            out = ops.conv5(dz16, plan, chans[1], wd, None, ops.ACT_NONE, dz_amax, mirror=True, tag="dgrad")
+        else:
+            out = ops.blur_gemm(dx, chans[1], first_nbr_t(), plan.n_in_rows, wd, None, ops.ACT_NONE, tag="dgrad", x_amax=dz_amax)
+    if not keep_fp32:
+        ops.release_zero_rows(dx)
+    return out, grads
+
+
 def backward(dx, xs, chans, layers, n_rows, first_nbr, first_nbr_t, need_input_grad, need_param_grad,
-             first_row_scale=None, amaxs=None, first5=None):
+             first_row_scale=None, amaxs=None, first5=None, dz_bound=None):
     """dx: gradient w.r.t. the stack's (post-activation) output, vertex-major, modified in place.
     first_nbr_t: callable returning the transposed table of the first layer (built lazily).
+    dz_bound: (slot a, slot b) with max|dx| <= a x b, and dx taken from ops.zero_rows (one-layer stacks on engine 5).
     Returns (dx_in or None, [(dw (F, C, Co), db (Co)) or None per layer])."""
+    if dz_bound is not None and first5 is not None and len(layers) == 1 and amaxs:
+        return _backward_single_layer5(dx, xs, chans, layers[0], first_nbr_t, need_input_grad, need_param_grad[0], amaxs,
+                                       first5, dz_bound)
     grads = [None] * len(layers)
     for l in range(len(layers) - 1, -1, -1):
         w, b, act = layers[l]

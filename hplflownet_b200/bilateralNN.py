@@ -97,7 +97,7 @@ class _BCLFunction(torch.autograd.Function):
         h = nbr2.size(1)
         layers = [(kernel_weight(params[2 * l]), params[2 * l + 1].detach(), acts[l]) for l in range(len(acts))]
         plan = _plan_for_first_layer(nbr2, c_in, layers[0][0].size(2))
-        inv, first5, lat = None, None, None
+        inv, first5, lat, wsum_amax = None, None, None, None
         # the producer of the lattice rows records max|rows| (or a bound of it) itself: no separate absmax pass
         lat_amax = ops.amax_slots(feat.device, 1) if (ops.fused_stats() and (c_in % 4 == 0 or plan is not None)) else None
         if do_splat:
@@ -105,9 +105,14 @@ class _BCLFunction(torch.autograd.Function):
             if plan is not None and use_norm:
                 # engine 5: the normalised rows only ever exist as their pre-split image.  |S[v]| <= max|feat| (a convex
                 # combination, bilateralNN.py:150-186), so the splat kernel's fused max|feat| is a valid operand scale.
-                raw, wsum = ops.scatter_rows(feat, bary_i, off_i, h, True, in_amax=lat_amax)
-                x16 = ops.h16b_split(raw, c_in, lat_amax, norm=wsum)
-                inv = ops.reciprocal_(wsum)
+                # One pass turns the accumulators into the normalised image, writes 1 / (wsum + 1e-5) for the backward, records
+                # max wsum and zeroes the accumulator again (it returns to the zero pool: no memset per call).
+                raw = ops.zero_rows(h, c_in, feat.device)
+                raw, wsum = ops.scatter_rows(feat, bary_i, off_i, h, True, in_amax=lat_amax, rows=raw)
+                inv = torch.empty_like(wsum)
+                wsum_amax = ops.amax_slots(feat.device, 1)
+                x16 = ops.h16b_split_ex(raw, c_in, lat_amax, norm=wsum, inv_out=inv, norm_amax_out=wsum_amax, dispose=2)
+                ops.release_zero_rows(raw)
                 first5 = _stack.First5(x16, lat_amax, plan)
             else:
                 lat, wsum = ops.scatter_rows(feat, bary_i, off_i, h, use_norm)
@@ -137,6 +142,10 @@ class _BCLFunction(torch.autograd.Function):
         ctx.cfg, ctx.chans, ctx.h = cfg, chans, h
         ctx.xs, ctx.layers, ctx.inv, ctx.first5 = xs, layers, inv, first5
         ctx.amaxs = amaxs
+        # max of the weight sums, valid for the OUT tables when they are the in tables (slice backward bound, see backward)
+        same_tables = (do_splat and do_slice and out_bary.data_ptr() == in_bary.data_ptr() and out_off.data_ptr() == in_off.data_ptr()
+                       and out_bary.shape == in_bary.shape)
+        ctx.wsum_amax = wsum_amax if same_tables else None
         ctx.idx = (bary_i, off_i, nbr2, bary_o, off_o)
         ctx.has_slice_bias = slice_bias is not None
         ctx.param_shapes = [p.shape for p in params]
@@ -149,8 +158,17 @@ class _BCLFunction(torch.autograd.Function):
         chans, h, xs, layers = ctx.chans, ctx.h, ctx.xs, ctx.layers
         g = grad_out[0].contiguous()
         d_slice_bias = None
+        dz_bound = None
         if do_slice:
-            dx, _ = ops.scatter_rows(g, bary_o, off_o, h, False)
+            if ctx.first5 is not None and len(layers) == 1 and ctx.wsum_amax is not None:
+                # |dz[v]| <= max|g| x (sum of barycentric weights at v): the splat's fused max|g| and the forward's max wsum
+                # give the operand scale of dz without a pass over it; the accumulator comes from the zero pool
+                g_amax = ops.amax_slots(g.device, 1)
+                dx = ops.zero_rows(h, chans[-1], g.device)
+                dx, _ = ops.scatter_rows(g, bary_o, off_o, h, False, in_amax=g_amax, rows=dx)
+                dz_bound = (g_amax, ctx.wsum_amax)
+            else:
+                dx, _ = ops.scatter_rows(g, bary_o, off_o, h, False)
             if ctx.has_slice_bias and ctx.needs_input_grad[7]:
                 d_slice_bias = ops.channel_sums(g)
         else:
@@ -159,7 +177,7 @@ class _BCLFunction(torch.autograd.Function):
         need_feat = ctx.needs_input_grad[1]
         need_param = [ctx.needs_input_grad[8 + 2 * l] or ctx.needs_input_grad[9 + 2 * l] for l in range(len(layers))]
         dx, pg = _stack.backward(dx, xs, chans, layers, h, nbr2, lambda: ops.transpose_table(nbr2, h),
-                                 need_feat, need_param, amaxs=ctx.amaxs, first5=ctx.first5)
+                                 need_feat, need_param, amaxs=ctx.amaxs, first5=ctx.first5, dz_bound=dz_bound)
         grads = []
         for l, g_l in enumerate(pg):
             if g_l is None:

@@ -186,6 +186,115 @@ __global__ void h16b_split_kernel(const float* __restrict__ x, long long ld, lon
     dst[4] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// The same split with the passes around it folded in (one trip over the rows instead of three or four):
+//   forward : x = splat accumulators, norm = weight sums -> normalised image, inv_out[v] = 1 / (norm[v] + 1e-5) (for the
+//             backward of the splat), norm_amax_out <- max norm (bound of the slice-backward magnitudes, see below);
+//   backward: x = dz, y = the layer's saved output -> x *= act'(y), image of the result, colsum += column sums (bias
+//             gradient); the operand scale comes from *amax_a (exact maximum) or from the BOUND *amax_a x *amax_b
+//             (|dz[v]| <= max|g| x sum of barycentric weights at v for a slice backward) so that no separate max pass is
+//             needed; amax_out <- the value the image was scaled with (what the contraction kernels read).
+//   dispose : 0 keep x, 1 write the act'-scaled values back (a consumer still needs fp32 rows), 2 zero x (the buffer goes
+//             back to the zero pool: the next splat accumulates into it without a memset).
+__device__ __forceinline__ uint32_t bound_bits(const uint32_t* a, const uint32_t* b) {
+    const uint32_t ba = __ldg(a);
+    if (b == nullptr) return ba;
+    const uint32_t bb = __ldg(b);
+    if (ba == 0 || bb == 0) return 0;
+    int e = (int)((ba >> 23) & 0xff) + (int)((bb >> 23) & 0xff) - 254 + 2;           // a < 2^(ea+1), b < 2^(eb+1): a b < 2^(ea+eb+2)
+    e = e < -126 ? -126 : (e > 126 ? 126 : e);
+    return (uint32_t)(e + 127) << 23;
+}
+
+__global__ void __launch_bounds__(256)
+h16b_split_fused_kernel(float* __restrict__ x, long long ld, long long n_rows, int channels, int cb_count,
+                        const float* __restrict__ norm, float* __restrict__ inv_out, uint32_t* __restrict__ norm_amax_out,
+                        const float* __restrict__ y, long long ld_y, float slope, const uint32_t* __restrict__ amax_a,
+                        const uint32_t* __restrict__ amax_b, uint32_t* __restrict__ amax_out, float* __restrict__ colsum,
+                        int dispose, uint4* __restrict__ out) {
+    __shared__ float part[256][9];
+    const int cpr = cb_count * 4;                                         // 8-channel groups per row
+    const int rows_per_iter = 256 / cpr;
+    const int r_in = threadIdx.x / cpr, g = threadIdx.x - r_in * cpr;
+    const bool worker = r_in < rows_per_iter;
+    const int c0 = g * 8;
+    const uint32_t bits = bound_bits(amax_a, amax_b);
+    if (amax_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *amax_out = bits;
+    float s, inv_s;
+    scale_from_amax(bits, s, inv_s);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    float n_max = 0.f;
+    for (long long row = (long long)blockIdx.x * rows_per_iter + r_in; worker && row < n_rows; row += (long long)gridDim.x * rows_per_iter) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        float* p = x + row * ld + c0;
+        const bool full8 = c0 + 8 <= channels;
+        if (full8) {
+            const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (c0 + i < channels) v[i] = p[i];
+        }
+        if (norm != nullptr) {
+            const float w = __ldg(norm + row);
+            const float r = 1.0f / (w + 1e-5f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] *= r;                         // same rounding as normalize_rows_kernel
+            if (g == 0) {
+                if (inv_out != nullptr) inv_out[row] = r;
+                n_max = fmaxf(n_max, w);
+            }
+        }
+        if (y != nullptr) {
+            const float* py = y + row * ld_y + c0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (c0 + i < channels) v[i] *= __ldg(py + i) > 0.f ? 1.f : slope;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += v[i];
+        if (dispose != 0) {
+            const float z = dispose == 2 ? 0.f : 1.f;
+            if (full8) {
+                *reinterpret_cast<float4*>(p) = make_float4(v[0] * z, v[1] * z, v[2] * z, v[3] * z);
+                *reinterpret_cast<float4*>(p + 4) = make_float4(v[4] * z, v[5] * z, v[6] * z, v[7] * z);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (c0 + i < channels) p[i] = v[i] * z;
+            }
+        }
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split2(v[2 * i] * inv_s, v[2 * i + 1] * inv_s, hi[i], lo[i]);
+        uint4* dst = out + (row * cb_count + (g >> 2)) * 8 + (g & 3);
+        dst[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        dst[4] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    if (norm_amax_out != nullptr) {                                       // (block-uniform condition)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n_max = fmaxf(n_max, __shfl_xor_sync(0xffffffffu, n_max, o));
+        if ((threadIdx.x & 31) == 0 && n_max > 0.f && __float_as_uint(n_max) > *reinterpret_cast<volatile uint32_t*>(norm_amax_out))
+            atomicMax(norm_amax_out, __float_as_uint(n_max));
+    }
+    if (colsum != nullptr) {                                              // (block-uniform condition)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) part[threadIdx.x][i] = worker ? acc[i] : 0.f;
+        __syncthreads();
+        if (threadIdx.x < cpr * 8) {                                      // one thread per channel slot of the (padded) row
+            const int gg = threadIdx.x >> 3, i = threadIdx.x & 7;
+            float t = 0.f;
+            for (int r = 0; r < rows_per_iter; ++r) t += part[r * cpr + gg][i];
+            const int c = gg * 8 + i;
+            if (c < channels) atomicAdd(colsum + c, t);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------- weight image
 // w[f, c, o] (strided) -> per (cb, stage = tap pair): two 8 KB tiles; tile rows n = 0..127 are [W_hi(o = n) ; W_lo(o = n - 64)],
 // K = 32 channels of block cb, K-major no-swizzle: chunk kc at kc * 2048 + (n / 8) * 128 + (n % 8) * 16.
@@ -844,6 +953,26 @@ int hpl_h16b_split(const float* x, int64_t ld, int64_t n_rows, int64_t channels,
     const long long work = n_rows * cb * 4;
     h16b_split_kernel<<<(unsigned)((work + 255) / 256), 256, 0, as_stream(stream)>>>(x, ld, n_rows, (int)channels, cb, norm, amax,
                                                                                   reinterpret_cast<uint4*>(x16));
+    HPL_RETURN_LAST();
+}
+
+int hpl_h16b_split_ex(float* x, int64_t ld, int64_t n_rows, int64_t channels, const float* norm, float* inv_out,
+                      uint32_t* norm_amax_out, const float* y, int64_t ld_y, int act, const uint32_t* amax_a,
+                      const uint32_t* amax_b, uint32_t* amax_out, float* colsum, int dispose, void* x16, void* stream) {
+    HPL_CHECK_ARG((x || n_rows == 0) && amax_a && x16 && channels > 0 && ld >= channels && ld % 4 == 0);
+    HPL_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)x16 & 15) == 0 && dispose >= 0 && dispose <= 2);
+    HPL_CHECK_ARG(act == HPL_ACT_NONE || (y != nullptr && ld_y >= channels));
+    HPL_CHECK_ARG(cb_of(channels) * 4 <= 256);
+    if (n_rows == 0) return 0;
+    const int cb = cb_of(channels);
+    const int rows_per_iter = 256 / (cb * 4);
+    long long blocks = (n_rows + rows_per_iter - 1) / rows_per_iter;
+    const long long cap = 8LL * num_sms();                                // grid-stride: few atomics per column sum
+    if (blocks > cap) blocks = cap;
+    const float slope = act == HPL_ACT_LEAKY ? HPL_LEAKY_RATE : 0.f;
+    h16b_split_fused_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+        x, ld, n_rows, (int)channels, cb, norm, inv_out, norm_amax_out, act == HPL_ACT_NONE ? nullptr : y, ld_y, slope, amax_a, amax_b,
+        amax_out, colsum, dispose, reinterpret_cast<uint4*>(x16));
     HPL_RETURN_LAST();
 }
 

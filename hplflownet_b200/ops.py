@@ -163,13 +163,38 @@ def alloc_rows(n_rows, channels, device, zero=False):
     return torch.empty((n_rows, ld), dtype=torch.float32, device=device)
 
 
-def scatter_rows(x, bary, off, n_rows, want_wsum, in_amax=None):
+# Zero pool: splat accumulators (rows that fp32 RED adds into) must start at zero.  A buffer whose last consumer zeroes it
+# again (hpl_h16b_split_ex with dispose = 2) goes back to the pool and the next splat of the same shape reuses it without
+# a memset (62 MB per cfg2 x 32 step and direction).  Keyed by (device, stream, rows, ld).
+_zero_pool = {}
+
+
+def zero_rows(n_rows, channels, device):
+    """(n_rows, round4(channels)) fp32, all zero."""
+    ld = round4(channels)
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, n_rows, ld)
+    free = _zero_pool.get(key)
+    if free:
+        return free.pop()
+    return torch.zeros((n_rows, ld), dtype=torch.float32, device=device)
+
+
+def release_zero_rows(t):
+    """Give back a buffer that is all zero again (its consumer ran with dispose = 2 on the current stream)."""
+    key = (t.device.index, torch.cuda.current_stream(t.device).cuda_stream, t.size(0), t.size(1))
+    free = _zero_pool.setdefault(key, [])
+    if len(free) < 4:
+        free.append(t)
+
+
+def scatter_rows(x, bary, off, n_rows, want_wsum, in_amax=None, rows=None):
     """x (C, N), bary (4, N), off (4, N) -> rows (n_rows, ld) [, wsum (n_rows)].  in_amax: zeroed slot that receives
-    max|x| (a bound of the normalised splat's magnitude)."""
+    max|x| (a bound of the normalised splat's magnitude).  rows: a zeroed accumulator to use (ops.zero_rows)."""
     _f32(x, "x"); _f32(bary, "bary")
     off, i64 = _idx(off, "off")
     c, n = x.shape
-    rows = alloc_rows(n_rows, c, x.device, zero=True)
+    if rows is None:
+        rows = alloc_rows(n_rows, c, x.device, zero=True)
     wsum = torch.zeros(n_rows, dtype=torch.float32, device=x.device) if want_wsum else None
     with _timed("scatter"):
         _lib.call("hpl_scatter_rows", x.data_ptr(), bary.data_ptr(), off.data_ptr(), i64, n, c,
@@ -467,3 +492,17 @@ def wgrad5(x16, dz16, plan, c_in, c_out, x_amax, dz_amax):
         _lib.call("hpl_wgrad5", x16.data_ptr(), dz16.data_ptr(), plan.buf.data_ptr(), plan.n_rows, plan.filter_size,
                   c_in, c_out, dw.data_ptr(), x_amax.data_ptr(), dz_amax.data_ptr(), _stream())
     return dw
+
+
+def h16b_split_ex(x, channels, amax_a, norm=None, inv_out=None, norm_amax_out=None, y=None, act=ACT_NONE, amax_b=None,
+                  amax_out=None, colsum=None, dispose=0):
+    """h16b image of x with the surrounding passes folded in (include/hplflownet_b200.h: hpl_h16b_split_ex)."""
+    _f32(x, "x")
+    n = x.size(0)
+    buf = torch.empty(max(_lib.load().hpl_h16b_bytes(n, channels), 16), dtype=torch.uint8, device=x.device)
+    ptr = lambda t: t.data_ptr() if t is not None else None      # noqa: E731
+    has_y = y is not None and act != ACT_NONE
+    _lib.call("hpl_h16b_split_ex", x.data_ptr(), x.stride(0), n, channels, ptr(norm), ptr(inv_out), ptr(norm_amax_out),
+              y.data_ptr() if has_y else None, y.stride(0) if has_y else 0, act if has_y else ACT_NONE,
+              amax_a.data_ptr(), ptr(amax_b), ptr(amax_out), ptr(colsum), dispose, buf.data_ptr(), _stream())
+    return buf

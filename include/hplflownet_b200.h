@@ -189,6 +189,20 @@ int64_t hpl_h16b_bytes(int64_t n_rows, int64_t channels);
 int hpl_h16b_split(const float* x, int64_t ld, int64_t n_rows, int64_t channels, const float* norm,
                    const uint32_t* amax, void* x16, void* stream);
 
+/* The same split with its neighbouring passes folded in (one trip over the rows).  All optional pointers may be NULL.
+ *   norm / inv_out / norm_amax_out : density normalisation as above; inv_out[v] <- 1/(norm[v]+1e-5) (not aliasing norm);
+ *                                    norm_amax_out (zeroed slot) <- bit pattern of max norm;
+ *   y, ld_y, act                   : x[v,c] *= (y[v,c] > 0 ? 1 : slope(act)) first (activation backward, module_utils.py:34);
+ *   amax_a, amax_b, amax_out       : operand scale from *amax_a, or from the bound *amax_a x *amax_b when amax_b != NULL
+ *                                    (slice backward: |dz[v]| <= max|g| x sum of barycentric weights at v);
+ *                                    amax_out <- the value used, for the contraction kernels that read the image;
+ *   colsum                         : += column sums of the (act'-scaled) rows (bias gradient), zeroed by the caller;
+ *   dispose                        : 0 keep x, 1 write the act'-scaled rows back, 2 zero x (reuse as a splat accumulator). */
+int hpl_h16b_split_ex(float* x, int64_t ld, int64_t n_rows, int64_t channels, const float* norm, float* inv_out,
+                      uint32_t* norm_amax_out, const float* y, int64_t ld_y, int act, const uint32_t* amax_a,
+                      const uint32_t* amax_b, uint32_t* amax_out, float* colsum, int dispose, void* x16,
+                      void* stream);
+
 /* out[row,:] = act(bias + sum_f x[nbr[f,row]] . w[f]) over the plan's table; x16 = h16b image of x (n_in_rows, c_in).
  * w element (f,c,o) at w + f*w_sf + c*w_sc + o*w_so; tap_map (device, F int32, may be NULL): kernel tap g uses
  * w[tap_map[g]] (data gradient: mirrored tap, transposed weight).  workspace: hpl_conv5_workspace(c_in) bytes,

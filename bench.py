@@ -555,20 +555,23 @@ def train_leg(dev, rank, world, steps=4, warmup=2):
         ok = int(flag.item()) if ok else 0
     if not ok:
         return {"error": err or "failed on another rank"}
+    model.zero_grad(set_to_none=True)
+    buckets = T.GradBuckets(model.parameters(), bucket_mb=16.0)      # overlapped, copy-free gradient averaging
     for _ in range(warmup):
-        T.train_step(model, opt, gen, pairs, collate_batch1)
+        T.train_step(model, opt, gen, pairs, collate_batch1, buckets)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        loss = T.train_step(model, opt, gen, pairs, collate_batch1)
+        loss = T.train_step(model, opt, gen, pairs, collate_batch1, buckets)
     e1.record()
     torch.cuda.synchronize()
     (ms,) = sharding.max_over_ranks([e0.elapsed_time(e1)], device=dev)
     return {"workload": "HPLFlowNet train step: %d pairs (8192+8192 pts, 7 scales) per step over %d GPU(s), GPU lattice "
-                        "build + forward + EPE3D + backward + flat gradient all-reduce + Adam" % (TRAIN_PAIRS_PER_STEP, world),
+                        "build + forward + EPE3D + backward + bucketed gradient all-reduce overlapped with the last backward + Adam" % (TRAIN_PAIRS_PER_STEP, world),
+            "gradient_buckets": len(buckets.buckets),
             "value": TRAIN_PAIRS_PER_STEP * steps / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms / steps,
             "scaling": "strong", "steps": steps, "warmup": warmup, "loss_finite": bool(torch.isfinite(loss)),
             "params": sum(p.numel() for p in model.parameters())}
@@ -655,6 +658,8 @@ def corr_leg(dev):
         if gy is None:
             gy = torch.randn_like(y)
         y.backward(gy)
+    from hplflownet_b200 import ops
+    from hplflownet_b200.graphs import GraphedStep
     for _ in range(5):
         step()
     torch.cuda.synchronize()
@@ -666,9 +671,43 @@ def corr_leg(dev):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    return {"workload": "BilateralCorrelationFlex(3,1,1,64,[32,32],[64,64],prev_corr_dim=64) fwd+bwd, 8192+8192 pts, scale 1.0",
-            "ms_per_pair": ms, "pairs_per_s": 1e3 / ms, "H1": h1, "H2": h2,
-            "note": "the reference materialises 172.8 KB per vertex for this layer (bnn_flow.py:189-199)"}
+    out = {"workload": "BilateralCorrelationFlex(3,1,1,64,[32,32],[64,64],prev_corr_dim=64) fwd+bwd, 8192+8192 pts, scale 1.0",
+           "ms_per_pair_eager": ms, "H1": h1, "H2": h2,
+           "note": "the reference materialises 172.8 KB per vertex for this layer (bnn_flow.py:189-199)"}
+    # per-kernel durations of the two patch-correlation kernels (CUDA events, separate pass) and their roofline: both move
+    # F * P * width * 4 bytes per vertex between L2 and the SMs (the factored first layer's (H, P * width) operands stay in L2)
+    ops.PROFILE_GEMM, ops.PROFILE_ROWS = [], True
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize()
+    ev = {}
+    for tag, a, b in ops.PROFILE_GEMM:
+        ev.setdefault(tag, []).append(a.elapsed_time(b))
+    ops.PROFILE_GEMM, ops.PROFILE_ROWS = None, False
+    peaks = measured_peaks()
+    l2_bytes = 15.0 * 15.0 * 32 * 4 * h1 * 2                      # gathers from t1 (P rows) and t2 (F * P rows) per vertex, width 32
+    roof = {}
+    for tag in ("corr_gather", "corr_scatter"):
+        if tag in ev:
+            t = sum(ev[tag]) / len(ev[tag])
+            roof[tag] = {"kernel_ms": t, "l2_to_sm_bytes": l2_bytes, "achieved_gbs": l2_bytes / (t * 1e-3) / 1e9,
+                         "peak_gbs": peaks["hbm_gbs"], "frac": l2_bytes / (t * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                         "bound": "hbm (L2-resident gather; the denominator is the measured HBM copy peak)"}
+    out["roofline"] = roof
+    try:
+        g = GraphedStep(step)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(50):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        out["ms_per_pair"] = e0.elapsed_time(e1) / 50
+        out["launch"] = "one CUDA-graph replay per pair"
+    except Exception as e:                                       # noqa: BLE001
+        out["ms_per_pair"], out["launch"] = ms, "eager (graph capture failed: %s: %s)" % (type(e).__name__, e)
+    out["pairs_per_s"] = 1e3 / out["ms_per_pair"]
+    return out
 
 
 def lattice_leg(dev):

@@ -77,9 +77,10 @@ class _CorrFunction(torch.autograd.Function):
         t2 = ops.blur_gemm(s2, c, None, h2, wb, None, ops.ACT_NONE)     # (H2, P*wp)
         b0p = _pad_cols(b0.detach()[None], wp)[0].contiguous()
         z = torch.empty((h1 * filt, wp), dtype=torch.float32, device=dev)
-        _lib.call("hpl_corr_gather", t1.data_ptr(), t1.stride(0), i1c.data_ptr(), t2.data_ptr(), t2.stride(0),
-                  i2c.data_ptr(), int(i1c.dtype == torch.int64), b0p.data_ptr(), corr_acts[0], z.data_ptr(),
-                  z.stride(0), wp, patch, filt, h1, h1, h2, ops._stream())
+        with ops._timed("corr_gather"):
+            _lib.call("hpl_corr_gather", t1.data_ptr(), t1.stride(0), i1c.data_ptr(), t2.data_ptr(), t2.stride(0),
+                      i2c.data_ptr(), int(i1c.dtype == torch.int64), b0p.data_ptr(), corr_acts[0], z.data_ptr(),
+                      z.stride(0), wp, patch, filt, h1, h1, h2, ops._stream())
         del t1, t2
 
         # ---- remaining 1x1x1 corr layers on (H1*F, O) rows
@@ -147,9 +148,10 @@ class _CorrFunction(torch.autograd.Function):
         ops.act_backward_(dz, z, o1, corr_acts[0])
         dt1 = torch.zeros((h1, patch * wp), dtype=torch.float32, device=dev)
         dt2 = torch.zeros((h2, patch * wp), dtype=torch.float32, device=dev)
-        _lib.call("hpl_corr_scatter", dz.data_ptr(), dz.stride(0), i1c.data_ptr(), i2c.data_ptr(),
-                  int(i1c.dtype == torch.int64), dt1.data_ptr(), dt1.stride(0), dt2.data_ptr(), dt2.stride(0),
-                  wp, patch, filt, h1, h1, h2, ops._stream())
+        with ops._timed("corr_scatter"):
+            _lib.call("hpl_corr_scatter", dz.data_ptr(), dz.stride(0), i1c.data_ptr(), i2c.data_ptr(),
+                      int(i1c.dtype == torch.int64), dt1.data_ptr(), dt1.stride(0), dt2.data_ptr(), dt2.stride(0),
+                      wp, patch, filt, h1, h1, h2, ops._stream())
         if need(0) or need(1):
             dwa, _ = ops.blur_wgrad(s1, c1, None, h1, dt1, patch * wp, 1, want_db=False)     # (1, C1, P*wp)
             dwb, _ = ops.blur_wgrad(s2, c, None, h2, dt2, patch * wp, 1, want_db=False)      # (1, C,  P*wp)

@@ -65,7 +65,13 @@ scatter_rows_kernel(const float* __restrict__ x, const float* __restrict__ bary,
         if (row >= n_rows) row = -1;                     // out-of-range offsets are dropped (the reference would raise)
         s_off[r][lane] = row;
     }
-    if (in_amax != nullptr) block_absmax_to(x_max, in_amax);   // fused max|x| (operand-scale bound of the splatted rows)
+    if (in_amax != nullptr) {                                // fused max|x| (operand-scale bound of the splatted rows), per warp
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x_max = fmaxf(x_max, __shfl_xor_sync(0xffffffffu, x_max, o));
+        // (the plain read may be stale, but the scalar only grows: skipping is safe and almost every warp skips)
+        if (lane == 0 && x_max > 0.f && __float_as_uint(x_max) > *reinterpret_cast<volatile uint32_t*>(in_amax))
+            atomicMax(in_amax, __float_as_uint(x_max));
+    }
     __syncthreads();
 
     if (wsum != nullptr && blockIdx.y == 0 && threadIdx.x < 4 * kPts) {

@@ -123,7 +123,7 @@ class _timed:
         self.tag = tag
 
     def __enter__(self):
-        self.on = PROFILE_GEMM is not None and (PROFILE_ROWS or self.tag not in ("scatter", "gather"))
+        self.on = PROFILE_GEMM is not None and (PROFILE_ROWS or self.tag not in ("scatter", "gather", "corr_gather", "corr_scatter"))
         if self.on:
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e1 = torch.cuda.Event(enable_timing=True)

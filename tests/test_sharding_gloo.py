@@ -108,3 +108,48 @@ def test_flat_gradient_allreduce_averages_over_ranks(tmp_path):
     for k, (got, w) in enumerate(zip(res[0]["grads"], want)):
         if k != 3:
             assert torch.allclose(got, w, rtol=1e-6, atol=1e-7)
+
+
+def _bucket_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hplflownet_b200.train import GradBuckets
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3), torch.nn.Linear(3, 2))
+    unused = torch.nn.Parameter(torch.ones(4))                   # takes part in no loss on any rank
+    params = list(net.parameters()) + [unused]
+    buckets = GradBuckets(params, bucket_mb=1e-4)                # ~26 floats per bucket: several buckets
+    assert len(buckets.buckets) >= 3
+    res = []
+    for step in range(2):                                        # two steps: the views are reused
+        buckets.zero_()
+        for i in range(2):                                       # two local "pairs" per step, accumulated
+            if i == 1:
+                buckets.arm()
+            x = torch.full((2, 5), float(rank + 1 + i + step))
+            (net(x).sum() / 2).backward()
+        buckets.finish()
+        res.append([None if p.grad is None else p.grad.clone() for p in params])
+    torch.save(res, os.path.join(out_dir, "b%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+def test_bucketed_overlapped_gradient_allreduce(tmp_path):
+    world, port = 2, 29617
+    mp.spawn(_bucket_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(tmp_path / ("b%d.pt" % r)) for r in range(world)]
+    for step in range(2):
+        for a, b in zip(res[0][step], res[1][step]):
+            assert (a is None and b is None) or torch.equal(a, b)
+        assert res[0][step][-1] is None                          # the untouched parameter keeps grad = None
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3), torch.nn.Linear(3, 2))
+        want = [torch.zeros_like(p) for p in net.parameters()]
+        for r in range(world):
+            for i in range(2):
+                net.zero_grad()
+                (net(torch.full((2, 5), float(r + 1 + i + step))).sum() / 2).backward()
+                for w, p in zip(want, net.parameters()):
+                    w += p.grad / world
+        for got, w in zip(res[0][step], want):
+            assert torch.allclose(got, w, rtol=1e-6, atol=1e-7)

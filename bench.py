@@ -618,6 +618,20 @@ def model_leg(dev):
                 y = run(build)
             torch.cuda.synchronize()
             out[name] = 1e3 * (time.perf_counter() - t0) / reps
+    # the same forward (resident lattice) as ONE CUDA-graph replay: what is left is kernel time
+    try:
+        from hplflownet_b200.graphs import GraphedStep
+        with ops.weight_cache_scope():
+            g = GraphedStep(lambda: run(False))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(20):
+                g.replay()
+            torch.cuda.synchronize()
+            out["forward_graph_ms"] = 1e3 * (time.perf_counter() - t0) / 20
+    except Exception as e:                                       # noqa: BLE001
+        out["forward_graph_ms"] = None
+        out["forward_graph_error"] = "%s: %s" % (type(e).__name__, e)
     out.update({"workload": "HPLFlowNet forward, 8192+8192-pt pair, 7 scales, evaluate mode, random weights",
                 "pairs_per_s": 1e3 / out["build_plus_forward_ms"], "output_finite": bool(torch.isfinite(y).all()),
                 "note": "reference CPU forward: 13.8 s/pair + 4.1-4.9 s lattice build (SURVEY §6, 8 vCPU)"})

@@ -71,13 +71,16 @@ def _backward_single_layer5(dx, xs, chans, layer, first_nbr_t, need_input_grad, 
     x_amax, x16 = amaxs[0]
     dgrad5 = need_input_grad and plan.symmetric and ops.conv5_supported(w.size(0), chans[1], chans[0])
     keep_fp32 = need_input_grad and not dgrad5                     # engine 2 will gather fp32 rows
-    db = dx.new_zeros(chans[1]) if (need_param_grad and b is not None) else None
-    dz_amax = ops.amax_slots(dx.device, 1)
+    arena = dz_bound[2] if len(dz_bound) > 2 else None                 # pre-zeroed small outputs (one fill for all of them)
+    db = None
+    if need_param_grad and b is not None:
+        db = arena["db"] if arena is not None else dx.new_zeros(chans[1])
+    dz_amax = arena["dz_amax"] if arena is not None else ops.amax_slots(dx.device, 1)
     dz16 = ops.h16b_split_ex(dx, chans[1], dz_bound[0], y=xs[1] if act != ops.ACT_NONE else None, act=act,
                              amax_b=dz_bound[1], amax_out=dz_amax, colsum=db, dispose=1 if keep_fp32 else 2)
     grads = [None]
     if need_param_grad:
-        grads[0] = (ops.wgrad5(x16, dz16, plan, chans[0], chans[1], x_amax, dz_amax), db)
+        grads[0] = (ops.wgrad5(x16, dz16, plan, chans[0], chans[1], x_amax, dz_amax, out=arena["dw"] if arena is not None else None), db)
     out = None
     if need_input_grad:
         wd = w.transpose(1, 2)                                    # (F, Co, C) view
@@ -97,7 +100,8 @@ def backward(dx, xs, chans, layers, n_rows, first_nbr, first_nbr_t, need_input_g
              first_row_scale=None, amaxs=None, first5=None, dz_bound=None):
     """dx: gradient w.r.t. the stack's (post-activation) output, vertex-major, modified in place.
     first_nbr_t: callable returning the transposed table of the first layer (built lazily).
-    dz_bound: (slot a, slot b) with max|dx| <= a x b, and dx taken from ops.zero_rows (one-layer stacks on engine 5).
+    dz_bound: (slot a, slot b[, arena]) with max|dx| <= a x b, and dx taken from ops.zero_rows (one-layer stacks on engine 5);
+    arena: ops.zero_arena with "dz_amax", "dw", "db" pieces.
     Returns (dx_in or None, [(dw (F, C, Co), db (Co)) or None per layer])."""
     if dz_bound is not None and first5 is not None and len(layers) == 1 and amaxs:
         return _backward_single_layer5(dx, xs, chans, layers[0], first_nbr_t, need_input_grad, need_param_grad[0], amaxs,

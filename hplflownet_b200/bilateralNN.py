@@ -99,7 +99,9 @@ class _BCLFunction(torch.autograd.Function):
         plan = _plan_for_first_layer(nbr2, c_in, layers[0][0].size(2))
         inv, first5, lat, wsum_amax = None, None, None, None
         # the producer of the lattice rows records max|rows| (or a bound of it) itself: no separate absmax pass
-        lat_amax = ops.amax_slots(feat.device, 1) if (ops.fused_stats() and (c_in % 4 == 0 or plan is not None)) else None
+        fused_first = plan is not None and do_splat and use_norm     # (that path takes its slots from one zeroed arena)
+        lat_amax = (ops.amax_slots(feat.device, 1)
+                    if (ops.fused_stats() and (c_in % 4 == 0 or plan is not None) and not fused_first) else None)
         if do_splat:
             bary_i, off_i = in_bary[0].contiguous(), in_off[0].contiguous()
             if plan is not None and use_norm:
@@ -108,9 +110,10 @@ class _BCLFunction(torch.autograd.Function):
                 # One pass turns the accumulators into the normalised image, writes 1 / (wsum + 1e-5) for the backward, records
                 # max wsum and zeroes the accumulator again (it returns to the zero pool: no memset per call).
                 raw = ops.zero_rows(h, c_in, feat.device)
-                raw, wsum = ops.scatter_rows(feat, bary_i, off_i, h, True, in_amax=lat_amax, rows=raw)
+                z = ops.zero_arena(feat.device, [("wsum", h, torch.float32), ("x_amax", 1, torch.int32), ("w_amax", 1, torch.int32)])
+                lat_amax, wsum_amax = z["x_amax"], z["w_amax"]
+                raw, wsum = ops.scatter_rows(feat, bary_i, off_i, h, True, in_amax=lat_amax, rows=raw, wsum=z["wsum"])
                 inv = torch.empty_like(wsum)
-                wsum_amax = ops.amax_slots(feat.device, 1)
                 x16 = ops.h16b_split_ex(raw, c_in, lat_amax, norm=wsum, inv_out=inv, norm_amax_out=wsum_amax, dispose=2)
                 ops.release_zero_rows(raw)
                 first5 = _stack.First5(x16, lat_amax, plan)
@@ -163,14 +166,17 @@ class _BCLFunction(torch.autograd.Function):
             if ctx.first5 is not None and len(layers) == 1 and ctx.wsum_amax is not None:
                 # |dz[v]| <= max|g| x (sum of barycentric weights at v): the splat's fused max|g| and the forward's max wsum
                 # give the operand scale of dz without a pass over it; the accumulator comes from the zero pool
-                g_amax = ops.amax_slots(g.device, 1)
+                w0 = layers[0][0]
+                arena = ops.zero_arena(g.device, [("g_amax", 1, torch.int32), ("dz_amax", 1, torch.int32),
+                                                  ("dw", w0.numel(), torch.float32), ("db", chans[-1], torch.float32),
+                                                  ("dsb", chans[-1], torch.float32)])
                 dx = ops.zero_rows(h, chans[-1], g.device)
-                dx, _ = ops.scatter_rows(g, bary_o, off_o, h, False, in_amax=g_amax, rows=dx)
-                dz_bound = (g_amax, ctx.wsum_amax)
+                dx, _ = ops.scatter_rows(g, bary_o, off_o, h, False, in_amax=arena["g_amax"], rows=dx)
+                dz_bound = (arena["g_amax"], ctx.wsum_amax, arena)
             else:
                 dx, _ = ops.scatter_rows(g, bary_o, off_o, h, False)
             if ctx.has_slice_bias and ctx.needs_input_grad[7]:
-                d_slice_bias = ops.channel_sums(g)
+                d_slice_bias = ops.channel_sums(g, out=dz_bound[2]["dsb"] if dz_bound is not None else None)
         else:
             dx = ops.cm_to_rows(g)
 

@@ -187,20 +187,34 @@ def release_zero_rows(t):
         free.append(t)
 
 
-def scatter_rows(x, bary, off, n_rows, want_wsum, in_amax=None, rows=None):
+def scatter_rows(x, bary, off, n_rows, want_wsum, in_amax=None, rows=None, wsum=None):
     """x (C, N), bary (4, N), off (4, N) -> rows (n_rows, ld) [, wsum (n_rows)].  in_amax: zeroed slot that receives
-    max|x| (a bound of the normalised splat's magnitude).  rows: a zeroed accumulator to use (ops.zero_rows)."""
+    max|x| (a bound of the normalised splat's magnitude).  rows / wsum: zeroed accumulators to use (ops.zero_rows,
+    ops.zero_arena)."""
     _f32(x, "x"); _f32(bary, "bary")
     off, i64 = _idx(off, "off")
     c, n = x.shape
     if rows is None:
         rows = alloc_rows(n_rows, c, x.device, zero=True)
-    wsum = torch.zeros(n_rows, dtype=torch.float32, device=x.device) if want_wsum else None
+    if want_wsum and wsum is None:
+        wsum = torch.zeros(n_rows, dtype=torch.float32, device=x.device)
     with _timed("scatter"):
         _lib.call("hpl_scatter_rows", x.data_ptr(), bary.data_ptr(), off.data_ptr(), i64, n, c,
                   rows.data_ptr(), rows.stride(0), n_rows, wsum.data_ptr() if want_wsum else None,
                   in_amax.data_ptr() if in_amax is not None else None, _stream())
     return rows, wsum
+
+
+def zero_arena(device, spec):
+    """One zero-filled allocation carved into named tensors: spec = [(name, numel, dtype)], every piece 16-byte aligned.
+    A step needs a handful of small zeroed outputs (statistic slots, weight sums, dw, bias gradients); one fill kernel
+    instead of one per tensor keeps them off the launch path."""
+    offs, total = [], 0
+    for _, n, _ in spec:
+        offs.append(total)
+        total += (int(n) + 3) // 4 * 4
+    buf = torch.zeros(max(total, 4), dtype=torch.float32, device=device)
+    return {name: buf[o:o + int(n)].view(dt) for (name, n, dt), o in zip(spec, offs)}
 
 
 def amax_slots(device, n):
@@ -429,10 +443,11 @@ def rows_to_cm(rows, channels):
     return cm
 
 
-def channel_sums(x):
+def channel_sums(x, out=None):
+    """Row sums of x (C, N); out: a zeroed (C,) tensor to accumulate into."""
     _f32(x, "x")
     c, n = x.shape
-    s = torch.zeros(c, dtype=torch.float32, device=x.device)
+    s = out if out is not None else torch.zeros(c, dtype=torch.float32, device=x.device)
     _lib.call("hpl_channel_sums", x.data_ptr(), c, n, s.data_ptr(), _stream())
     return s
 
@@ -484,10 +499,12 @@ def conv5(x16, plan, c_in, w, bias, act, x_amax, out=None, out_amax=None, mirror
     return out
 
 
-def wgrad5(x16, dz16, plan, c_in, c_out, x_amax, dz_amax):
-    """Engine 5 weight gradient: dw (F, C, Co) = sum_v x[nbr[f, v]]^T dz[v] over plan's table (h16b images in)."""
+def wgrad5(x16, dz16, plan, c_in, c_out, x_amax, dz_amax, out=None):
+    """Engine 5 weight gradient: dw (F, C, Co) = sum_v x[nbr[f, v]]^T dz[v] over plan's table (h16b images in).
+    out: a zeroed (F * C * Co,) buffer to accumulate into."""
     assert plan.usable
-    dw = torch.zeros((plan.filter_size, c_in, c_out), dtype=torch.float32, device=x16.device)
+    dw = (out.view(plan.filter_size, c_in, c_out) if out is not None
+          else torch.zeros((plan.filter_size, c_in, c_out), dtype=torch.float32, device=x16.device))
     with _timed("wgrad"):
         _lib.call("hpl_wgrad5", x16.data_ptr(), dz16.data_ptr(), plan.buf.data_ptr(), plan.n_rows, plan.filter_size,
                   c_in, c_out, dw.data_ptr(), x_amax.data_ptr(), dz_amax.data_ptr(), _stream())

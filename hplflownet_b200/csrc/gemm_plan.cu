@@ -573,9 +573,12 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
         for (int k = 0; k < n_my; ++k) {
             const int t = t_begin + k;
             const int row = __ldg(p.tile_rows + (long long)t * TM + q * 32 + lane);
+            const bool tre = p.trace != nullptr && blockIdx.x == 0 && q == 0 && lane == 0 && k < 64;
+            if (tre) p.trace[2048 + 4 * k] = clock64();
             if (lane == 0) wait_bar(acc_full + 8 * acc, pacc);
             __syncwarp();
             fence_after();
+            if (tre) p.trace[2048 + 4 * k + 1] = clock64();
             const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_cols);
 #pragma unroll 1
             for (int c0 = 0; c0 < 64; c0 += 16) {
@@ -623,6 +626,7 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
             fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_a(acc_empty + 8 * acc);
+            if (tre) p.trace[2048 + 4 * k + 2] = clock64();
             if (++acc == acc_stages) { acc = 0; pacc ^= 1; }
         }
         if (p.out_amax != nullptr) {

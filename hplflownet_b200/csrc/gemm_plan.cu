@@ -146,6 +146,34 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     return v;
 }
 
+// tcgen05.mma with the A operand in tensor memory (M = 128: lane = row, every 32-bit column = two consecutive K elements)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 registers of every lane -> 32 consecutive tensor-memory columns of the warp's lane quarter
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint4* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0].x), "r"(v[0].y), "r"(v[0].z), "r"(v[0].w), "r"(v[1].x), "r"(v[1].y), "r"(v[1].z), "r"(v[1].w),
+        "r"(v[2].x), "r"(v[2].y), "r"(v[2].z), "r"(v[2].w), "r"(v[3].x), "r"(v[3].y), "r"(v[3].z), "r"(v[3].w),
+        "r"(v[4].x), "r"(v[4].y), "r"(v[4].z), "r"(v[4].w), "r"(v[5].x), "r"(v[5].y), "r"(v[5].z), "r"(v[5].w),
+        "r"(v[6].x), "r"(v[6].y), "r"(v[6].z), "r"(v[6].w), "r"(v[7].x), "r"(v[7].y), "r"(v[7].z), "r"(v[7].w)
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// one row of the output tile: shared memory -> global memory through the bulk-copy engine (no LSU store transactions)
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------- h16b image
 // x (n_rows, ld) fp32 vertex-major -> (n_rows, CB) lines of [32 hi | 32 lo] halves, CB = ceil(C / 32); channels beyond C
 // are zero.  norm != nullptr: x[v, :] is first multiplied by 1 / (norm[v] + 1e-5) (density normalisation,
@@ -356,7 +384,14 @@ struct Conv5Args {
 // while the tensor core drains the first.  Measured on the previous structure (two-tap stages, ring of 2): a slot's
 // copy -> MMA -> copy chain carries ~1750 cycles of hand-over latency per round trip, so per-stage time was
 // latency + copy + MMA, not their maximum; four slots in flight hide it.
-template <int F>
+// AT: the A operand lives in TENSOR MEMORY: every copy thread owns one row of the tile, reads its staged row from shared
+// memory (chunk order rotated by the lane so that a quarter warp hits 8 different bank groups, un-rotated in registers) and
+// writes it with tcgen05.st; the MMA then fetches only the weight tile from shared memory (71 -> 39 KB of shared-memory
+// traffic per tap-stage).  The shared memory the A stages no longer need stages the output tile, which leaves through the
+// bulk-copy engine (one 256-byte row per instruction) instead of 32-lines-per-instruction LSU stores.  Tensor memory:
+// accumulators [0, 256), A slots [256, 384): the accumulators are single-buffered in this mode, so the epilogue frees them
+// as soon as they are in registers / shared memory.
+template <int F, bool AT>
 __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * kC5Slots + 4 + 4];
@@ -365,7 +400,7 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t u_base = smem_base;                                   // 2 x kUBuf
-    const uint32_t a_base = u_base + 2 * kUBuf;                          // kC5Slots x kATap
+    const uint32_t a_base = u_base + 2 * kUBuf;                          // kC5Slots x kATap; AT: the output staging tile instead
     const uint32_t b_base = a_base + kC5Slots * kATap;                   // kC5Slots x kBTap
     const uint32_t idx_base = b_base + kC5Slots * kBTap;                 // 2 x kIdxBuf
     const uint32_t bar0 = smem_u32(bars);
@@ -380,7 +415,9 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
     const int n_phases = n_my * CB;
     const int n_stages = n_phases * F;
     const int acc_cols = 2 * p.n_main * 128;                             // TMEM columns of one tile: two issuers x n_main x [main | cross]
-    const int acc_stages = 2 * acc_cols <= 512 ? 2 : 1;
+    const int acc_stages = (!AT && 2 * acc_cols <= 512) ? 2 : 1;
+    constexpr uint32_t kTmemA = 256;                                     // AT: first column of the A slots (32 columns each)
+    constexpr uint32_t kOutPitch = 64 * 4 + 16;                          // AT: staged output row (272 B: odd multiple of 16 -> conflict-free)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kC5Slots; ++s) { mbar_init(&bars[s], 1); mbar_init(&bars[kC5Slots + s], 1); }
@@ -442,7 +479,23 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
             if (tr) trp[0] = clock64();
             uint32_t slot[8];
             uint4 v[8];
-            if (!(p.dbg & 1)) {
+            if (AT) {
+                // thread = tile row gt: its staged row, 8 chunks in lane-rotated order (conflict-free), then un-rotated
+                if (!(p.dbg & 1)) {
+                    const uint32_t sl = lds_u16(idx_base + (k & 1) * kIdxBuf + (tap * TM + gt) * 2);
+                    const uint32_t src = u_base + (ph & 1) * kUBuf + sl * kURow;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = lds128(src + (((i + lane) & 7) << 4));
+#pragma unroll
+                    for (int b = 1; b < 8; b <<= 1) {                      // v[i] holds chunk (i + lane) % 8: rotate by the set bits of lane % 8
+                        uint4 t[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) t[i] = (lane & b) ? v[(i - b) & 7] : v[i];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = t[i];
+                    }
+                }
+            } else if (!(p.dbg & 1)) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) slot[i] = lds_u16(ibs + tap * (TM * 2) + i * 32);
 #pragma unroll
@@ -459,13 +512,21 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
             }
             asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kC5GroupWarps * 32) : "memory");
             if (tr) trp[1] = clock64();
-            if (!(p.dbg & 1)) {
+            if (AT) {
+                if (!(p.dbg & 1)) {
+                    fence_after();                                       // (the slot's previous MMAs, observed through `empty`)
+                    tmem_st32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + kTmemA + grp * 32, v);
+                }
+                fence_before();
+            } else {
+                if (!(p.dbg & 1)) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) sts128(abd + i * 256, v[i].x, v[i].y, v[i].z, v[i].w);
+                    for (int i = 0; i < 8; ++i) sts128(abd + i * 256, v[i].x, v[i].y, v[i].z, v[i].w);
+                }
+                if (!(p.dbg & 32)) fence_proxy_async();
             }
             if (tr) trp[2] = clock64();
             if (tr) trp[3] = clock64();
-            if (!(p.dbg & 32)) fence_proxy_async();
             asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kC5GroupWarps * 32) : "memory");
             if (gt == 0) {
                 if (p.dbg & 4) mbar_arrive_a(full_g);
@@ -548,8 +609,14 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
                             const uint32_t ah = a16 + ((j * 2 * kA_LBO) >> 4);
                             const uint32_t bb = b16 + ((j * 2 * kB_LBO) >> 4);
                             const uint32_t dg = d0 + (uint32_t)(g * 128);
-                            umma_f16(dg, kDescA | ah, kDescB | bb, kIdescMain, g == pg);                   // x_hi . [W_hi | W_lo]
-                            umma_f16(dg + 64, kDescA | (ah + (kAPlane >> 4)), kDescB | bb, kIdescLo, 1);   // x_lo . W_hi
+                            if (AT) {
+                                const uint32_t at = tmem_d + kTmemA + (uint32_t)(slot_i * 32 + 8 * j);
+                                umma_f16_ts(dg, at, kDescB | bb, kIdescMain, g == pg);                     // x_hi . [W_hi | W_lo]
+                                umma_f16_ts(dg + 64, at + 16, kDescB | bb, kIdescLo, 1);                   // x_lo . W_hi
+                            } else {
+                                umma_f16(dg, kDescA | ah, kDescB | bb, kIdescMain, g == pg);               // x_hi . [W_hi | W_lo]
+                                umma_f16(dg + 64, kDescA | (ah + (kAPlane >> 4)), kDescB | bb, kIdescLo, 1);   // x_lo . W_hi
+                            }
                             pg = g;
                         }
                     }
@@ -934,8 +1001,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad5_kernel(const Wgrad5Args p)
 void set_attrs() {
     static bool done = false;
     if (done) return;
-    cudaFuncSetAttribute(conv5_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    cudaFuncSetAttribute(conv5_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(conv5_kernel<15, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(conv5_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(conv5_kernel<15, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(conv5_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     cudaFuncSetAttribute(wgrad5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmem);
     done = true;
 }
@@ -1029,8 +1098,16 @@ int hpl_conv5(const void* x16, const void* plan, int64_t n_out_rows, int64_t fil
     a.trace = nullptr;
     { const char* e = getenv("HPL_CONV5_TRACE"); if (e) a.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0)); }
     const unsigned grid = (unsigned)(a.n_tiles < num_sms() ? a.n_tiles : num_sms());
-    if (filter_size == 15) conv5_kernel<15><<<grid, kC5Threads, kSmem, s>>>(a);
-    else conv5_kernel<16><<<grid, kC5Threads, kSmem, s>>>(a);
+    static int at_knob = -1;                                 // HPL_CONV5_TMEM=0/1: A operand from shared / tensor memory
+    if (at_knob < 0) { const char* e = getenv("HPL_CONV5_TMEM"); at_knob = e ? atoi(e) : 0; }
+    const bool rows_ok = ld_out % 4 == 0 && c_out % 4 == 0;   // (bulk row stores: 16-byte multiples)
+    if (at_knob && a.n_main == 1 && rows_ok) {
+        if (filter_size == 15) conv5_kernel<15, true><<<grid, kC5Threads, kSmem, s>>>(a);
+        else conv5_kernel<16, true><<<grid, kC5Threads, kSmem, s>>>(a);
+    } else {
+        if (filter_size == 15) conv5_kernel<15, false><<<grid, kC5Threads, kSmem, s>>>(a);
+        else conv5_kernel<16, false><<<grid, kC5Threads, kSmem, s>>>(a);
+    }
     HPL_RETURN_LAST();
 }
 

@@ -396,6 +396,7 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * kC5Slots + 4 + 4];
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float bias_s[64];                           // bias (zero beyond c_out / without one)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -434,6 +435,10 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
     if (threadIdx.x < 16) {
         const uint32_t z = u_base + (threadIdx.x >> 3) * kUBuf + kUmax * kURow + (threadIdx.x & 7) * 16;
         sts128(z, 0, 0, 0, 0);
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 128) {
+        const int o = threadIdx.x - 64;
+        bias_s[o] = (p.bias != nullptr && o < p.c_out) ? __ldg(p.bias + o) : 0.f;
     }
     fence_before();
     __syncthreads();
@@ -647,37 +652,82 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
             fence_after();
             if (tre) p.trace[2048 + 4 * k + 1] = clock64();
             const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_cols);
+            // the staging row of this thread (AT): the previous tile's bulk store must have read it
+            if (AT) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            const uint32_t stage_row = a_base + (uint32_t)(q * 32 + lane) * kOutPitch;
+            const int n_sets = 2 * p.n_main;                                 // (issuer, main accumulator) -> 128 columns [main | cross]
 #pragma unroll 1
             for (int c0 = 0; c0 < 64; c0 += 16) {
                 if (c0 >= p.c_out) break;
                 float sum[16];
-                uint32_t v[16];
-                // accumulator sets of the tile: (issuer, main accumulator) -> 128 columns [main | cross]
-                const int n_sets = 2 * p.n_main;
-                tmem_ld16(taddr + 64 + c0, v);                               // cross terms
+                if (AT && n_sets == 2) {                                     // two loads in flight per wait
+                    uint32_t v0[16], v1[16];
+                    tmem_ld16_nowait(taddr + 64 + c0, v0);                   // cross, issuer 0
+                    tmem_ld16_nowait(taddr + 128 + 64 + c0, v1);             // cross, issuer 1
+                    tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) sum[j] = __uint_as_float(v[j]);
-                for (int g = 1; g < n_sets; ++g) {
-                    tmem_ld16(taddr + g * 128 + 64 + c0, v);
+                    for (int j = 0; j < 16; ++j) sum[j] = (__uint_as_float(v0[j]) + __uint_as_float(v1[j])) * kLoInv;
+                    tmem_ld16_nowait(taddr + c0, v0);                        // main, issuer 0
+                    tmem_ld16_nowait(taddr + 128 + c0, v1);                  // main, issuer 1
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) sum[j] += __uint_as_float(v[j]);
-                }
+                    for (int j = 0; j < 16; ++j) sum[j] += __uint_as_float(v0[j]) + __uint_as_float(v1[j]);
+                } else {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + 64 + c0, v);                           // cross terms
 #pragma unroll
-                for (int j = 0; j < 16; ++j) sum[j] *= kLoInv;
-                for (int g = 0; g < n_sets; ++g) {
-                    tmem_ld16(taddr + g * 128 + c0, v);
+                    for (int j = 0; j < 16; ++j) sum[j] = __uint_as_float(v[j]);
+                    for (int g = 1; g < n_sets; ++g) {
+                        tmem_ld16(taddr + g * 128 + 64 + c0, v);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) sum[j] += __uint_as_float(v[j]);
-                }
-                if (row >= 0 && !(p.dbg & 16)) {
-                    float y[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int o = c0 + j;
-                        const float b = (p.bias != nullptr && o < p.c_out) ? __ldg(p.bias + o) : 0.f;
-                        y[j] = apply_act(fmaf(sum[j], s_ab, b), p.act);
-                        if (o < p.c_out) y_max = fmaxf(y_max, fabsf(y[j]));
+                        for (int j = 0; j < 16; ++j) sum[j] += __uint_as_float(v[j]);
                     }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sum[j] *= kLoInv;
+                    for (int g = 0; g < n_sets; ++g) {
+                        tmem_ld16(taddr + g * 128 + c0, v);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) sum[j] += __uint_as_float(v[j]);
+                    }
+                }
+                if (p.dbg & 16) continue;
+                // bias + activation + max|y|: chunk-uniform branches only (a per-element switch / bound test version spent
+                // ~5.5k cycles per tile here -- longer than the tensor-memory reads)
+                float y[16];
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 b = *reinterpret_cast<const float4*>(bias_s + c0 + j);
+                    y[j] = fmaf(sum[j], s_ab, b.x);
+                    y[j + 1] = fmaf(sum[j + 1], s_ab, b.y);
+                    y[j + 2] = fmaf(sum[j + 2], s_ab, b.z);
+                    y[j + 3] = fmaf(sum[j + 3], s_ab, b.w);
+                }
+                if (p.act == HPL_ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) y[j] = y[j] > 0.f ? y[j] : 0.f;
+                } else if (p.act == HPL_ACT_LEAKY) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) y[j] = y[j] > 0.f ? y[j] : HPL_LEAKY_RATE * y[j];
+                }
+                if (row >= 0) {
+                    float m = 0.f;
+                    if (c0 + 16 <= p.c_out) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) m = fmaxf(m, fabsf(y[j]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < p.c_out) m = fmaxf(m, fabsf(y[j]));
+                    }
+                    y_max = fmaxf(y_max, m);
+                }
+                if (AT) {                                                    // stage the row; it leaves by bulk copy after the release
+                    if (p.dbg & 64) continue;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        sts128(stage_row + (c0 + j) * 4, __float_as_uint(y[j]), __float_as_uint(y[j + 1]), __float_as_uint(y[j + 2]),
+                               __float_as_uint(y[j + 3]));
+                } else if (row >= 0) {
                     float* dst = p.out + (long long)row * p.ld_out + c0;
                     if (c0 + 15 < p.c_out) {
 #pragma unroll
@@ -693,6 +743,13 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
             fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_a(acc_empty + 8 * acc);
+            if (tre) p.trace[2048 + 4 * k + 3] = clock64();
+            if (AT && !(p.dbg & (16 | 128))) {                                   // the accumulators are free again; the row leaves asynchronously
+                fence_proxy_async();
+                if (row >= 0)
+                    bulk_store(p.out + (long long)row * p.ld_out, a_base + (uint32_t)(q * 32 + lane) * kOutPitch, (uint32_t)p.c_out * 4u);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
             if (tre) p.trace[2048 + 4 * k + 2] = clock64();
             if (++acc == acc_stages) { acc = 0; pacc ^= 1; }
         }
@@ -701,6 +758,7 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
             for (int o = 16; o > 0; o >>= 1) y_max = fmaxf(y_max, __shfl_xor_sync(0xffffffffu, y_max, o));
             if (lane == 0 && y_max > 0.f) atomicMax(p.out_amax, __float_as_uint(y_max));
         }
+        if (AT) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the last rows have left shared memory
     }
     fence_before();
     __syncthreads();
@@ -1098,8 +1156,8 @@ int hpl_conv5(const void* x16, const void* plan, int64_t n_out_rows, int64_t fil
     a.trace = nullptr;
     { const char* e = getenv("HPL_CONV5_TRACE"); if (e) a.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0)); }
     const unsigned grid = (unsigned)(a.n_tiles < num_sms() ? a.n_tiles : num_sms());
-    static int at_knob = -1;                                 // HPL_CONV5_TMEM=0/1: A operand from shared / tensor memory
-    if (at_knob < 0) { const char* e = getenv("HPL_CONV5_TMEM"); at_knob = e ? atoi(e) : 0; }
+    static int at_knob = -1;                                 // A operand from tensor memory (default) / HPL_CONV5_TMEM=0: shared memory
+    if (at_knob < 0) { const char* e = getenv("HPL_CONV5_TMEM"); at_knob = e ? atoi(e) : 1; }
     const bool rows_ok = ld_out % 4 == 0 && c_out % 4 == 0;   // (bulk row stores: 16-byte multiples)
     if (at_knob && a.n_main == 1 && rows_ok) {
         if (filter_size == 15) conv5_kernel<15, true><<<grid, kC5Threads, kSmem, s>>>(a);

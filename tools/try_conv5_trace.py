@@ -34,4 +34,4 @@ print("mma: wait-full %.0f  issue+commit %.0f" % tuple(((t[8:200, j + 1] - t[8:2
 
 print("epilogue per tile: [wait start, acc ready, done] relative to kernel start")
 for k in range(13):
-    print(k, [int(v) - t0 for v in te[k][:3]], "wait %d  work %d" % (int(te[k][1] - te[k][0]), int(te[k][2] - te[k][1])))
+    print(k, [int(v) - t0 for v in te[k][:3]], "wait %d  hold %d  work %d" % (int(te[k][1] - te[k][0]), int(te[k][3] - te[k][1]), int(te[k][2] - te[k][1])))

@@ -46,7 +46,9 @@ constexpr uint32_t kB_LBO = 128 * 16;            // weight tile: 128 N rows ([W_
 constexpr int kBTap = 4 * kB_LBO;                // 8192
 constexpr int kBStage = 2 * kBTap;
 constexpr int kStages = 2;
-constexpr int kC5Slots = 4;                      // forward kernel: ring of one-tap stages
+constexpr int kC5Slots = 4;                      // forward kernel: ring of one-tap stages (shared-memory A path) = number of copy groups
+constexpr int kC5SlotsT = 8;                     // ring on the tensor-memory A path (A slots in TMEM, 8 weight tiles in shared memory)
+constexpr int kC5OutStage = 128 * (64 * 4 + 16); // tensor-memory A path: staged output tile (272-byte rows)
 constexpr int kIdxBuf = kTaps * TM * 2;          // 4096 B of uint16 slots
 constexpr int kCopyWarps = 8, kCopyThreads = kCopyWarps * 32;      // weight-gradient kernel: one copy group
 constexpr int kMmaWarp = 8, kWWarp = 9;
@@ -59,7 +61,9 @@ constexpr int kC5MmaWarp = 16, kC5LoadWarp = 18, kC5LoadWarps = 2;  // warps 16,
 constexpr int kC5LoadThreads = kC5LoadWarps * 32;
 constexpr int kC5Threads = 24 * 32;
 constexpr int kC5UIters = (kUmax * 8 + kC5CopyThreads - 1) / kC5CopyThreads;   // 8 row-chunk copies per thread and phase
-constexpr int kSmem = 2 * kUBuf + kC5Slots * (kATap + kBTap) + 2 * kIdxBuf + 1024;
+constexpr int kC5RingBytes = kC5Slots * (kATap + kBTap) > kC5OutStage + kC5SlotsT * kBTap ? kC5Slots * (kATap + kBTap)
+                                                                                          : kC5OutStage + kC5SlotsT * kBTap;
+constexpr int kSmem = 2 * kUBuf + kC5RingBytes + 2 * kIdxBuf + 1024;
 constexpr int kUIters = (kUmax * 8 + kCopyThreads - 1) / kCopyThreads;      // 15 row-chunk copies per thread and phase
 constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
 static_assert(kSmem <= 232448, "shared memory budget");
@@ -394,18 +398,19 @@ struct Conv5Args {
 template <int F, bool AT>
 __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2 * kC5Slots + 4 + 4];
+    constexpr int NS = AT ? kC5SlotsT : kC5Slots;                        // ring slots (group g fills slots g, g + 4, ...)
+    __shared__ __align__(8) uint64_t bars[2 * kC5SlotsT + 4 + 4];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float bias_s[64];                           // bias (zero beyond c_out / without one)
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t u_base = smem_base;                                   // 2 x kUBuf
     const uint32_t a_base = u_base + 2 * kUBuf;                          // kC5Slots x kATap; AT: the output staging tile instead
-    const uint32_t b_base = a_base + kC5Slots * kATap;                   // kC5Slots x kBTap
-    const uint32_t idx_base = b_base + kC5Slots * kBTap;                 // 2 x kIdxBuf
+    const uint32_t b_base = a_base + (AT ? kC5OutStage : kC5Slots * kATap);   // NS x kBTap
+    const uint32_t idx_base = a_base + kC5RingBytes;                     // 2 x kIdxBuf
     const uint32_t bar0 = smem_u32(bars);
-    const uint32_t full = bar0, empty = full + 8 * kC5Slots, ufull = empty + 8 * kC5Slots, ufree = ufull + 16;
+    const uint32_t full = bar0, empty = full + 8 * NS, ufull = empty + 8 * NS, ufree = ufull + 16;
     const uint32_t acc_full = ufree + 16, acc_empty = acc_full + 16;
 
     const int per = (p.n_tiles + gridDim.x - 1) / gridDim.x;
@@ -415,18 +420,22 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
     const int CB = p.cb_count;
     const int n_phases = n_my * CB;
     const int n_stages = n_phases * F;
-    const int acc_cols = 2 * p.n_main * 128;                             // TMEM columns of one tile: two issuers x n_main x [main | cross]
-    const int acc_stages = (!AT && 2 * acc_cols <= 512) ? 2 : 1;
+    // MMA issuers: two on the shared-memory A path (alternate stages, own accumulators); ONE on the tensor-memory path, whose
+    // accumulators (128 columns per tile) are then double-buffered next to the A slots, so the epilogue of a tile
+    // overlaps the next tile's stages.
+    constexpr int NI = AT ? 1 : 2;
+    const int acc_cols = NI * p.n_main * 128;                            // TMEM columns of one tile: issuers x n_main x [main | cross]
+    const int acc_stages = (2 * acc_cols + (AT ? kC5SlotsT * 32 : 0) <= 512) ? 2 : 1;
     constexpr uint32_t kTmemA = 256;                                     // AT: first column of the A slots (32 columns each)
     constexpr uint32_t kOutPitch = 64 * 4 + 16;                          // AT: staged output row (272 B: odd multiple of 16 -> conflict-free)
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kC5Slots; ++s) { mbar_init(&bars[s], 1); mbar_init(&bars[kC5Slots + s], 1); }
+        for (int s = 0; s < NS; ++s) { mbar_init(&bars[s], 1); mbar_init(&bars[NS + s], 1); }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&bars[2 * kC5Slots + s], kC5LoadThreads);          // ufull: the phase's rows have landed
-            mbar_init(&bars[2 * kC5Slots + 2 + s], kC5CopyWarps);        // ufree: every copy warp is done reading the buffer
-            mbar_init(&bars[2 * kC5Slots + 4 + s], 2);                   // acc_full: both MMA issuers have committed the tile
-            mbar_init(&bars[2 * kC5Slots + 6 + s], 4);
+            mbar_init(&bars[2 * NS + s], 1);                            // ufull: the phase's rows have landed (one arrival for the loaders)
+            mbar_init(&bars[2 * NS + 2 + s], kC5Slots);            // ufree: every copy group is done reading the buffer
+            mbar_init(&bars[2 * NS + 4 + s], NI);                  // acc_full: every MMA issuer has committed the tile
+            mbar_init(&bars[2 * NS + 6 + s], 4);
         }
         fence_mbar_init();
     }
@@ -460,25 +469,28 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
         // A position of (row = i * 16 + rg, chunk c8): + i * 256
         const uint32_t dst_off = (c8 >> 2) * kAPlane + (c8 & 3) * kA_LBO + (rg >> 3) * 128 + (rg & 7) * 16;
         const uint32_t abd = a_base + grp * kATap + dst_off;
-        const uint32_t full_g = full + 8 * grp, empty_g = empty + 8 * grp;
 
         int ph = -1, k = 0, cb = 0;                                       // current phase and its (tile, channel block)
         int next_ph_tap0 = 0;                                            // stage number where the next phase starts
         uint32_t ub = 0, ibs = 0;
         for (int G = grp; G < n_stages; G += kC5Slots) {
             if (G >= next_ph_tap0) {                                     // this group's first stage of a new phase
+                // (the group's last bar.sync of the previous stage came after every one of its reads of that phase's rows)
                 if (ph >= 0) {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_a(ufree + 8 * (ph & 1));  // this warp is done reading the previous phase's rows
+                    if (gt == 0) mbar_arrive_a(ufree + 8 * (ph & 1));    // this group is done reading the previous phase's rows
                     if (++cb == CB) { cb = 0; ++k; }
                 }
                 ++ph;
                 next_ph_tap0 += F;
-                wait_bar(ufull + 8 * (ph & 1), (ph >> 1) & 1);
+                if (gt == 0) wait_bar(ufull + 8 * (ph & 1), (ph >> 1) & 1);
+                asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kC5GroupWarps * 32) : "memory");
                 ub = u_base + (ph & 1) * kUBuf + src_off;
                 ibs = idx_base + (k & 1) * kIdxBuf + idx_off;
             }
             const int tap = G - (next_ph_tap0 - F);
+            const int slot_g = G & (NS - 1);                                 // (NS == 4: always grp)
+            const uint32_t full_g = full + 8 * slot_g, empty_g = empty + 8 * slot_g;
+            const uint32_t par_g = (uint32_t)(G / NS) & 1;
             const bool tr = p.trace != nullptr && blockIdx.x == 0 && gt == 0 && G < 256;
             long long* trp = p.trace + G * 8;
             if (tr) trp[0] = clock64();
@@ -509,18 +521,19 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
             // One mbarrier wait and one arrival per GROUP and stage (named barriers inside the group): the SM's mbarrier
             // unit serialises its operations (~40 cycles each, measured: an empty pipeline with one wait + one arrival per
             // WARP ran at ~500 cycles per stage), so they are kept off the per-warp path.
+            if (tr) trp[1] = clock64() + (AT ? (v[0].x & 0) : 0);          // (the row reads have landed)
             if (gt == 0) {
-                wait_bar(empty_g, ((G >> 2) & 1) ^ 1);
+                wait_bar(empty_g, par_g ^ 1);
                 // the stage's weight tile (8 KB, one bulk copy) is requested by the group itself as soon as the slot is free
                 // (its complete_tx may land before the expect_tx below: the transaction count may go negative meanwhile)
-                if (!(p.dbg & 4)) bulk_load_a(b_base + grp * kBTap, p.w_image + ((long long)cb * kTaps + tap) * kBTap, kBTap, full_g);
+                if (!(p.dbg & 4)) bulk_load_a(b_base + slot_g * kBTap, p.w_image + ((long long)cb * kTaps + tap) * kBTap, kBTap, full_g);
             }
             asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kC5GroupWarps * 32) : "memory");
-            if (tr) trp[1] = clock64();
+            if (tr) trp[2] = clock64();
             if (AT) {
                 if (!(p.dbg & 1)) {
                     fence_after();                                       // (the slot's previous MMAs, observed through `empty`)
-                    tmem_st32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + kTmemA + grp * 32, v);
+                    tmem_st32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + kTmemA + slot_g * 32, v);
                 }
                 fence_before();
             } else {
@@ -530,7 +543,6 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
                 }
                 if (!(p.dbg & 32)) fence_proxy_async();
             }
-            if (tr) trp[2] = clock64();
             if (tr) trp[3] = clock64();
             asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kC5GroupWarps * 32) : "memory");
             if (gt == 0) {
@@ -551,7 +563,10 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
         int k = 0, cb = 0;
         for (int ph = 0; ph < n_phases; ++ph) {
             // the buffer held phase ph - 2: every copy warp has left it
-            if (ph >= 2) wait_bar(ufree + 8 * (ph & 1), ((ph - 2) >> 1) & 1);
+            if (ph >= 2) {
+                if (lt == 0) wait_bar(ufree + 8 * (ph & 1), ((ph - 2) >> 1) & 1);
+                asm volatile("bar.sync %0, %1;" ::"n"(kC5Slots + 1), "n"(kC5LoadThreads) : "memory");
+            }
             const int t = t_begin + k;
             const uint32_t ub = u_base + (ph & 1) * kUBuf + c8 * 16;
             if (cb == 0) {                                               // the tile's index block: 256 chunks of 16 B
@@ -573,66 +588,78 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
                         if (rows[i] >= 0) cp_async16(ub + (j0 + 8 * i) * kURow, src + (long long)rows[i] * row_bytes);
                 }
             }
-            cp_async_arrive_noinc(ufull + 8 * (ph & 1));
+            // one mbarrier arrival per phase (not one asynchronous arrival per thread): wait for the own copies, meet, arrive
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            asm volatile("bar.sync %0, %1;" ::"n"(kC5Slots + 1), "n"(kC5LoadThreads) : "memory");
+            if (lt == 0) mbar_arrive_a(ufull + 8 * (ph & 1));
             if (++cb == CB) { cb = 0; ++k; }
         }
-    } else if (warp == kC5MmaWarp || warp == kC5MmaWarp + 1) {
-        // ------------------------------------------------------------------ MMA issuers (one thread each)
-        // A lone thread needs ~80 cycles per tcgen05.mma (uniform-datapath descriptor arithmetic, R2UR, the ELECT wrapper)
-        // plus ~400 for the barrier wait and the commit of a stage -- more than the 96 cycles the tensor core needs for a K
-        // step, so ONE issuer caps the tensor pipe near 20 %.  Two issuers take alternate stages (issuer i: G % 2 == i,
-        // i.e. ring slots i and i + 2); each accumulates into its own TMEM columns (the order of tcgen05.mma between
-        // threads is not defined, and separate accumulators keep the result deterministic); the epilogue adds them.
-        if (lane == 0) {
+    } else if (warp == kC5MmaWarp || (NI == 2 && warp == kC5MmaWarp + 1)) {
+        // ------------------------------------------------------------------ MMA issuers
+        // The tensor core needs 64 / 32 cycles per K step of the N = 128 / N = 64 instruction (tools/umma_rate.cu: a tight
+        // issue loop reaches exactly that), 192 cycles per stage; what an issuer adds is its own instruction stream -- the
+        // barrier poll, the fence, descriptor arithmetic -- so that stream is kept short and warp-uniform.  On the
+        // shared-memory A path two issuers take alternate stages (issuer i: G % 2 == i); each accumulates into its own
+        // TMEM columns (the order of tcgen05.mma between threads is not defined, and separate accumulators keep the
+        // result deterministic); the epilogue adds them.
+        // The issuer warp stays converged and one elected lane issues (see elect_one in tc_common.cuh).
+        {
             const int me = warp - kC5MmaWarp;
             constexpr uint32_t kIdescMain = instr_desc(0, TM, 128, 0, 0);
             constexpr uint32_t kIdescLo = instr_desc(0, TM, 64, 0, 0);
             constexpr uint64_t kDescA = (uint64_t)((kA_LBO >> 4) & 0x3fff) << 16 | (uint64_t)(128 >> 4) << 32 | (uint64_t)1 << 46;
             constexpr uint64_t kDescB = (uint64_t)((kB_LBO >> 4) & 0x3fff) << 16 | (uint64_t)(128 >> 4) << 32 | (uint64_t)1 << 46;
             const int per_tile = CB * F;
+            const int n_main = AT ? 1 : p.n_main;
             int acc = 0;
             uint32_t pacc = 0;
             for (int k = 0; k < n_my; ++k) {
                 wait_bar(acc_empty + 8 * acc, pacc ^ 1);
                 fence_after();
-                const uint32_t d0 = tmem_d + (uint32_t)(acc * acc_cols + me * p.n_main * 128);
+                const uint32_t d0 = tmem_d + (uint32_t)(acc * acc_cols + me * n_main * 128);
                 const int G0 = k * per_tile;
                 int pg = -1;
-                for (int s = (G0 + me) & 1 ? 1 : 0; s < per_tile; s += 2) {   // stages of this tile with (G0 + s) % 2 == me
+                for (int s = NI == 2 ? ((G0 + me) & 1) : 0; s < per_tile; s += NI) {   // two issuers: stages with (G0 + s) % 2 == me
                     const int G = G0 + s;
-                    const int slot_i = G & (kC5Slots - 1);
-                    const bool tr = p.trace != nullptr && blockIdx.x == 0 && G < 256;
+                    const int slot_i = G & (NS - 1);
+                    const bool tr = p.trace != nullptr && blockIdx.x == 0 && G < 256 && lane == 0;
                     if (tr) p.trace[G * 8 + 5] = clock64();
-                    wait_bar(full + 8 * slot_i, (G >> 2) & 1);
+                    // (every lane polls: a lane-0 poll followed by __syncwarp() cost ~1000 cycles per stage)
+                    wait_bar(full + 8 * slot_i, (uint32_t)(G / NS) & 1);
                     fence_after();
                     if (tr) p.trace[G * 8 + 6] = clock64();
                     const uint32_t a16 = (a_base + slot_i * kATap) >> 4, b16 = (b_base + slot_i * kBTap) >> 4;
-                    if (!(p.dbg & 2)) {
+                    const int g0 = n_main == 1 ? 0 : ((2 * s) * n_main) / p.steps_total;         // main accumulator of the K steps
+                    const int g1 = n_main == 1 ? 0 : ((2 * s + 1) * n_main) / p.steps_total;
+                    if (elect_one()) {
+                        if (!(p.dbg & 2)) {
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const int g = p.n_main == 1 ? 0 : ((2 * s + j) * p.n_main) / p.steps_total;   // main accumulator of this K step
-                            const uint32_t ah = a16 + ((j * 2 * kA_LBO) >> 4);
-                            const uint32_t bb = b16 + ((j * 2 * kB_LBO) >> 4);
-                            const uint32_t dg = d0 + (uint32_t)(g * 128);
-                            if (AT) {
-                                const uint32_t at = tmem_d + kTmemA + (uint32_t)(slot_i * 32 + 8 * j);
-                                umma_f16_ts(dg, at, kDescB | bb, kIdescMain, g == pg);                     // x_hi . [W_hi | W_lo]
-                                umma_f16_ts(dg + 64, at + 16, kDescB | bb, kIdescLo, 1);                   // x_lo . W_hi
-                            } else {
-                                umma_f16(dg, kDescA | ah, kDescB | bb, kIdescMain, g == pg);               // x_hi . [W_hi | W_lo]
-                                umma_f16(dg + 64, kDescA | (ah + (kAPlane >> 4)), kDescB | bb, kIdescLo, 1);   // x_lo . W_hi
+                            for (int j = 0; j < 2; ++j) {
+                                const int g = j == 0 ? g0 : g1;
+                                const uint32_t ah = a16 + ((j * 2 * kA_LBO) >> 4);
+                                const uint32_t bb = b16 + ((j * 2 * kB_LBO) >> 4);
+                                const uint32_t dg = d0 + (uint32_t)(g * 128);
+                                if (AT) {
+                                    const uint32_t at = tmem_d + kTmemA + (uint32_t)(slot_i * 32 + 8 * j);
+                                    umma_f16_ts(dg, at, kDescB | bb, kIdescMain, g == pg);                 // x_hi . [W_hi | W_lo]
+                                    umma_f16_ts(dg + 64, at + 16, kDescB | bb, kIdescLo, 1);               // x_lo . W_hi
+                                } else {
+                                    umma_f16(dg, kDescA | ah, kDescB | bb, kIdescMain, g == pg);           // x_hi . [W_hi | W_lo]
+                                    umma_f16(dg + 64, kDescA | (ah + (kAPlane >> 4)), kDescB | bb, kIdescLo, 1);   // x_lo . W_hi
+                                }
+                                pg = g;
                             }
-                            pg = g;
                         }
+                        umma_commit_a(empty + 8 * slot_i);
                     }
-                    umma_commit_a(empty + 8 * slot_i);
+                    pg = g1;
                     if (tr) p.trace[G * 8 + 7] = clock64();
                 }
-                umma_commit_a(acc_full + 8 * acc);
+                if (elect_one()) umma_commit_a(acc_full + 8 * acc);
                 if (++acc == acc_stages) { acc = 0; pacc ^= 1; }
             }
         }
-    } else {
+    } else if (warp >= kC5LoadWarp + kC5LoadWarps) {
         // ------------------------------------------------------------------ epilogue (TMEM lane quarter = warp % 4)
         const int q = warp & 3;
         float s_in, inv_in, s_w, inv_w;
@@ -655,23 +682,18 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
             // the staging row of this thread (AT): the previous tile's bulk store must have read it
             if (AT) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             const uint32_t stage_row = a_base + (uint32_t)(q * 32 + lane) * kOutPitch;
-            const int n_sets = 2 * p.n_main;                                 // (issuer, main accumulator) -> 128 columns [main | cross]
+            const int n_sets = NI * p.n_main;                                // (issuer, main accumulator) -> 128 columns [main | cross]
 #pragma unroll 1
             for (int c0 = 0; c0 < 64; c0 += 16) {
                 if (c0 >= p.c_out) break;
                 float sum[16];
-                if (AT && n_sets == 2) {                                     // two loads in flight per wait
+                if (AT) {                                                    // one accumulator set: both loads in flight, one wait
                     uint32_t v0[16], v1[16];
-                    tmem_ld16_nowait(taddr + 64 + c0, v0);                   // cross, issuer 0
-                    tmem_ld16_nowait(taddr + 128 + 64 + c0, v1);             // cross, issuer 1
+                    tmem_ld16_nowait(taddr + 64 + c0, v0);                   // cross
+                    tmem_ld16_nowait(taddr + c0, v1);                        // main
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) sum[j] = (__uint_as_float(v0[j]) + __uint_as_float(v1[j])) * kLoInv;
-                    tmem_ld16_nowait(taddr + c0, v0);                        // main, issuer 0
-                    tmem_ld16_nowait(taddr + 128 + c0, v1);                  // main, issuer 1
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) sum[j] += __uint_as_float(v0[j]) + __uint_as_float(v1[j]);
+                    for (int j = 0; j < 16; ++j) sum[j] = fmaf(__uint_as_float(v0[j]), kLoInv, __uint_as_float(v1[j]));
                 } else {
                     uint32_t v[16];
                     tmem_ld16(taddr + 64 + c0, v);                           // cross terms

@@ -364,13 +364,40 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
                 for (int j = 0; j < 16; ++j) sum[j] += __uint_as_float(v[j]);
             }
             if (m < n_out_rows) {
+                // bias + activation + max|y| with chunk-uniform branches (per-element switch / bound tests cost more issue
+                // slots than the tensor-memory reads)
                 float y[16];
+                const bool full_chunk = o0 + cb + 16 <= c_out;
+                if (bias == nullptr) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int o = o0 + cb + j;
-                    const float b = (bias != nullptr && o < c_out) ? __ldg(bias + o) : 0.f;
-                    y[j] = apply_act(fmaf(sum[j], s_ab, b), act);
-                    if (o < c_out) y_max = fmaxf(y_max, fabsf(y[j]));
+                    for (int j = 0; j < 16; ++j) y[j] = sum[j] * s_ab;
+                } else if (full_chunk && ((uintptr_t)bias & 15) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + o0 + cb + j));
+                        y[j] = fmaf(sum[j], s_ab, b.x);
+                        y[j + 1] = fmaf(sum[j + 1], s_ab, b.y);
+                        y[j + 2] = fmaf(sum[j + 2], s_ab, b.z);
+                        y[j + 3] = fmaf(sum[j + 3], s_ab, b.w);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) y[j] = fmaf(sum[j], s_ab, o0 + cb + j < c_out ? __ldg(bias + o0 + cb + j) : 0.f);
+                }
+                if (act == HPL_ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) y[j] = y[j] > 0.f ? y[j] : 0.f;
+                } else if (act == HPL_ACT_LEAKY) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) y[j] = y[j] > 0.f ? y[j] : HPL_LEAKY_RATE * y[j];
+                }
+                if (full_chunk) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) y_max = fmaxf(y_max, fabsf(y[j]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (o0 + cb + j < c_out) y_max = fmaxf(y_max, fabsf(y[j]));
                 }
                 if (partial) {                                              // K split: add this CTA's partial tile (bias / act later)
                     if (!out_cm) {

@@ -48,6 +48,23 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
         "r"(parity), "r"(0x989680u)
         : "memory");
 }
+// One leader lane of a CONVERGED warp.  tcgen05.mma / tcgen05.commit take their operands from uniform registers: under a
+// plain `if (lane == 0)` the compiler cannot prove uniformity and wraps every such instruction in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop (~80 cycles per MMA on the issuing thread); inside
+// `if (elect_one())` of a warp-uniform region it emits the instruction directly.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+// warp index as a value the compiler knows to be warp-uniform
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 __device__ __forceinline__ void umma_commit_a(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }

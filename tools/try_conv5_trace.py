@@ -29,7 +29,7 @@ for i in range(0, 64):
     print(i, [int(v) - t0 for v in t[i]])
 d = t[1:200, 4] - t[0:199, 4]
 print("mean period between copy arrivals: %.0f clk" % d.float().mean().item())
-print("copy: wait-empty %.0f  copy %.0f  loads %.0f  fence+arrive %.0f" % tuple(((t[8:200, j + 1] - t[8:200, j]).float().mean().item()) for j in range(4)))
+print("copy: row reads %.0f  empty wait + W request + group barrier %.0f  tcgen05.st / STS %.0f  barrier+arrive %.0f" % tuple(((t[8:200, j + 1] - t[8:200, j]).float().mean().item()) for j in range(4)))
 print("mma: wait-full %.0f  issue+commit %.0f" % tuple(((t[8:200, j + 1] - t[8:200, j]).float().mean().item()) for j in (5, 6)))
 
 print("epilogue per tile: [wait start, acc ready, done] relative to kernel start")

@@ -828,7 +828,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad5_kernel(const Wgrad5Args p)
     __shared__ __align__(8) uint64_t bars[2 + 2 + 2 + 2 + 2];
     __shared__ uint32_t tmem_slot;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t u_base = smem_base;
     const uint32_t a_base = u_base + 2 * kUBuf;
@@ -986,8 +986,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad5_kernel(const Wgrad5Args p)
             asm volatile("bar.sync 1, %0;" ::"n"(kCopyThreads) : "memory");
         }
     } else if (warp == kMmaWarp) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer (converged warp, elected lane issues)
+        {
             constexpr uint32_t kIdescMain = instr_desc(0, TM, 128, 1, 1);
             constexpr uint32_t kIdescLo = instr_desc(0, TM, 64, 1, 1);
             constexpr uint64_t kDesc = (uint64_t)(128 >> 4) << 16 | (uint64_t)((kW_SBO >> 4) & 0x3fff) << 32 | (uint64_t)1 << 46;
@@ -1008,18 +1008,20 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad5_kernel(const Wgrad5Args p)
                         fence_after();
                         const uint32_t a16 = (a_base + stage * kWAStage) >> 4;
                         const uint32_t d = tmem_d + (uint32_t)(mt * 128);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint32_t acc = (since_flush | h | j) != 0;
-                            umma_f16(d, kDesc | (a16 + j * 16), kDesc | (b16 + j * 16), kIdescMain, acc);
-                            umma_f16(d + 64, kDesc | (a16 + (kWPlane >> 4) + j * 16), kDesc | (b16 + j * 16), kIdescLo, 1);
+                            for (int j = 0; j < 4; ++j) {
+                                const uint32_t acc = (since_flush | h | j) != 0;
+                                umma_f16(d, kDesc | (a16 + j * 16), kDesc | (b16 + j * 16), kIdescMain, acc);
+                                umma_f16(d + 64, kDesc | (a16 + (kWPlane >> 4) + j * 16), kDesc | (b16 + j * 16), kIdescLo, 1);
+                            }
+                            umma_commit_a(empty + 8 * stage);
                         }
-                        umma_commit_a(empty + 8 * stage);
                         if (++stage == 2) { stage = 0; phase_bit ^= 1; }
                     }
                 }
                 if (++since_flush == kFlushTiles || k == n_my - 1) {
-                    umma_commit_a(accb);
+                    if (elect_one()) umma_commit_a(accb);
                     since_flush = 0;
                 }
             }

@@ -182,7 +182,7 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
     __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], accum_bar;
     __shared__ uint32_t tmem_slot;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const long long m0 = (long long)blockIdx.x * TM;
     const int n_tile = blockIdx.y;
     const int n_kb_total = filter_size * kb_per_tap;
@@ -299,8 +299,10 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
             }
         }
     } else if (warp == kProducerWarps) {
-        if (lane == 0) {
-            // This single thread paces the CTA: no division per K block (g = floor(kb * n_main / n_kb) is tracked
+        // The issuer warp stays converged and one elected lane issues: under `if (lane == 0)` every tcgen05.mma / commit is
+        // wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~80 cycles per instruction on the issuing thread).
+        {
+            // This warp paces the CTA: no division per K block (g = floor(kb * n_main / n_kb) is tracked
             // incrementally) and descriptors built once per stage as a constant high word + a running address.
             int last_g = -1, stage = 0, g = 0, g_num = 0;
             uint32_t phase = 0;
@@ -312,21 +314,23 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
                 fence_after();
                 const uint32_t a_hi = (smem_base + stage * kStageBytes) >> 4;              // 16-byte units from here on
                 const uint32_t a_lo = a_hi + (kAHalf >> 4), b_hi = a_hi + (2 * kAHalf >> 4), b_lo = b_hi + (kBHalf >> 4);
+                if (elect_one()) {
 #pragma unroll
-                for (int j = 0; j < TK / 16; ++j) {
-                    const uint64_t dah = kDescA | (a_hi + j * (2 * kA_LBO >> 4)), dal = kDescA | (a_lo + j * (2 * kA_LBO >> 4));
-                    const uint64_t dbh = kDescB | (b_hi + j * (2 * kB_LBO >> 4)), dbl = kDescB | (b_lo + j * (2 * kB_LBO >> 4));
-                    umma_f16(tmem_d, dal, dbh, kIdescK, (kb | j) != 0);
-                    umma_f16(tmem_d, dah, dbl, kIdescK, 1);
-                    umma_f16(tmem_main, dah, dbh, kIdescK, g == last_g);
-                    last_g = g;
+                    for (int j = 0; j < TK / 16; ++j) {
+                        const uint64_t dah = kDescA | (a_hi + j * (2 * kA_LBO >> 4)), dal = kDescA | (a_lo + j * (2 * kA_LBO >> 4));
+                        const uint64_t dbh = kDescB | (b_hi + j * (2 * kB_LBO >> 4)), dbl = kDescB | (b_lo + j * (2 * kB_LBO >> 4));
+                        umma_f16(tmem_d, dal, dbh, kIdescK, (kb | j) != 0);
+                        umma_f16(tmem_d, dah, dbl, kIdescK, 1);
+                        umma_f16(tmem_main, dah, dbh, kIdescK, j == 0 ? g == last_g : 1);
+                    }
+                    umma_commit_a(empty_a + 8 * stage);
                 }
-                umma_commit_a(empty_a + 8 * stage);
+                last_g = g;
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
                 g_num += n_main;
                 if (g_num >= n_kb) { g_num -= n_kb; ++g; }
             }
-            umma_commit_a(accum_a);
+            if (elect_one()) umma_commit_a(accum_a);
         }
     } else {
         if (lane == 0) {
@@ -502,7 +506,7 @@ wgrad_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_r
     __shared__ __align__(8) uint64_t full_bar[kWStages], empty_bar[kWStages], accum_bar;
     __shared__ uint32_t tmem_slot;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     // blockIdx.x = M tile (fastest): the CTAs that share a vertex range -- and therefore its dz rows and most of its
     // gathered rows -- are launched together and hit L2 (ncu before: 350 MB of DRAM reads for 139 MB of operands)
     const int m0 = blockIdx.x * TM, o0 = blockIdx.z * TN;
@@ -648,7 +652,7 @@ wgrad_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_r
             }
         }
     } else if (warp == kProducerWarps) {
-        if (lane == 0) {
+        {                                                               // converged warp, elected lane issues (see the forward kernel)
             int last_g = -1, stage = 0, g = 0, g_num = 0;               // g = floor(kb * WG_MAIN / n_kb), incrementally
             uint32_t phase = 0;
             constexpr uint64_t kDescA = (uint64_t)((kWA_LBO >> 4) & 0x3fff) << 16 | (uint64_t)((kW_SBO >> 4) & 0x3fff) << 32 | (uint64_t)1 << 46;
@@ -659,21 +663,23 @@ wgrad_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_r
                 fence_after();
                 const uint32_t a_hi = (smem_base + stage * kWStageBytes) >> 4;             // 16-byte units from here on
                 const uint32_t a_lo = a_hi + (kWAHalf >> 4), b_hi = a_hi + (2 * kWAHalf >> 4), b_lo = b_hi + (kWBHalf >> 4);
+                if (elect_one()) {
 #pragma unroll
-                for (int j = 0; j < TK / 16; ++j) {                      // one MMA = 2 K groups of 8 vertices
-                    const uint64_t dah = kDescA | (a_hi + j * (2 * kWA_LBO >> 4)), dal = kDescA | (a_lo + j * (2 * kWA_LBO >> 4));
-                    const uint64_t dbh = kDescB | (b_hi + j * (2 * kWB_LBO >> 4)), dbl = kDescB | (b_lo + j * (2 * kWB_LBO >> 4));
-                    umma_f16(tmem_d, dal, dbh, kIdescMN, (kb | j) != 0);
-                    umma_f16(tmem_d, dah, dbl, kIdescMN, 1);
-                    umma_f16(tmem_main, dah, dbh, kIdescMN, g == last_g);
-                    last_g = g;
+                    for (int j = 0; j < TK / 16; ++j) {                  // one MMA = 2 K groups of 8 vertices
+                        const uint64_t dah = kDescA | (a_hi + j * (2 * kWA_LBO >> 4)), dal = kDescA | (a_lo + j * (2 * kWA_LBO >> 4));
+                        const uint64_t dbh = kDescB | (b_hi + j * (2 * kWB_LBO >> 4)), dbl = kDescB | (b_lo + j * (2 * kWB_LBO >> 4));
+                        umma_f16(tmem_d, dal, dbh, kIdescMN, (kb | j) != 0);
+                        umma_f16(tmem_d, dah, dbl, kIdescMN, 1);
+                        umma_f16(tmem_main, dah, dbh, kIdescMN, j == 0 ? g == last_g : 1);
+                    }
+                    umma_commit_a(empty_a + 8 * stage);
                 }
-                umma_commit_a(empty_a + 8 * stage);
+                last_g = g;
                 if (++stage == kWStages) { stage = 0; phase ^= 1; }
                 g_num += WG_MAIN;
                 if (g_num >= n_kb) { g_num -= n_kb; ++g; }
             }
-            umma_commit_a(accum_a);
+            if (elect_one()) umma_commit_a(accum_a);
         }
     }
 

@@ -395,8 +395,11 @@ struct Conv5Args {
 // bulk-copy engine (one 256-byte row per instruction) instead of 32-lines-per-instruction LSU stores.  Tensor memory:
 // accumulators [0, 256), A slots [256, 384): the accumulators are single-buffered in this mode, so the epilogue frees them
 // as soon as they are in registers / shared memory.
-template <int F, bool AT>
+// DBG: the instantiation with the experiment hooks (HPL_CONV5_DBG ablation bits, HPL_CONV5_TRACE clock stamps); the
+// production instantiation carries neither their tests nor their address arithmetic.
+template <int F, bool AT, bool DBG>
 __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p) {
+    const int dbg = DBG ? p.dbg : 0;
     extern __shared__ uint8_t smem_raw[];
     constexpr int NS = AT ? kC5SlotsT : kC5Slots;                        // ring slots (group g fills slots g, g + 4, ...)
     __shared__ __align__(8) uint64_t bars[2 * kC5SlotsT + 4 + 4];
@@ -462,6 +465,7 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
         const int tid = threadIdx.x;
         const int grp = tid >> 7;                                        // copy group = ring slot it fills (stages G % 4 == grp)
         const int gt = tid & 127;
+        const bool lead_warp = (warp & (kC5GroupWarps - 1)) == 0;        // the group's first warp (warp-uniform)
         const int c8 = gt & 7;                                           // 16-byte chunk of a 128-byte line
         const int rg = gt >> 3;                                          // 0..15: row within a group of 16
         const uint32_t src_off = c8 * 16;
@@ -482,7 +486,7 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
                 }
                 ++ph;
                 next_ph_tap0 += F;
-                if (gt == 0) wait_bar(ufull + 8 * (ph & 1), (ph >> 1) & 1);
+                if (lead_warp) wait_bar(ufull + 8 * (ph & 1), (ph >> 1) & 1);
                 asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kC5GroupWarps * 32) : "memory");
                 ub = u_base + (ph & 1) * kUBuf + src_off;
                 ibs = idx_base + (k & 1) * kIdxBuf + idx_off;
@@ -491,14 +495,14 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
             const int slot_g = G & (NS - 1);                                 // (NS == 4: always grp)
             const uint32_t full_g = full + 8 * slot_g, empty_g = empty + 8 * slot_g;
             const uint32_t par_g = (uint32_t)(G / NS) & 1;
-            const bool tr = p.trace != nullptr && blockIdx.x == 0 && gt == 0 && G < 256;
+            const bool tr = DBG && p.trace != nullptr && blockIdx.x == 0 && gt == 0 && G < 256;
             long long* trp = p.trace + G * 8;
             if (tr) trp[0] = clock64();
             uint32_t slot[8];
             uint4 v[8];
             if (AT) {
                 // thread = tile row gt: its staged row, 8 chunks in lane-rotated order (conflict-free), then un-rotated
-                if (!(p.dbg & 1)) {
+                if (!(dbg & 1)) {
                     const uint32_t sl = lds_u16(idx_base + (k & 1) * kIdxBuf + (tap * TM + gt) * 2);
                     const uint32_t src = u_base + (ph & 1) * kUBuf + sl * kURow;
 #pragma unroll
@@ -512,7 +516,7 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
                         for (int i = 0; i < 8; ++i) v[i] = t[i];
                     }
                 }
-            } else if (!(p.dbg & 1)) {
+            } else if (!(dbg & 1)) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) slot[i] = lds_u16(ibs + tap * (TM * 2) + i * 32);
 #pragma unroll
@@ -522,31 +526,35 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
             // unit serialises its operations (~40 cycles each, measured: an empty pipeline with one wait + one arrival per
             // WARP ran at ~500 cycles per stage), so they are kept off the per-warp path.
             if (tr) trp[1] = clock64() + (AT ? (v[0].x & 0) : 0);          // (the row reads have landed)
-            if (gt == 0) {
+            // The waiting is done by the group's whole first warp -- a warp-uniform branch.  (A single waiting lane leaves
+            // its warp diverged in front of the named barrier; that variant dead-locked in one build and, where it ran, cost
+            // ~1000 cycles per wait in the reconvergence.)
+            if (lead_warp) {
                 wait_bar(empty_g, par_g ^ 1);
                 // the stage's weight tile (8 KB, one bulk copy) is requested by the group itself as soon as the slot is free
                 // (its complete_tx may land before the expect_tx below: the transaction count may go negative meanwhile)
-                if (!(p.dbg & 4)) bulk_load_a(b_base + slot_g * kBTap, p.w_image + ((long long)cb * kTaps + tap) * kBTap, kBTap, full_g);
+                if (!(dbg & 4) && elect_one())
+                    bulk_load_a(b_base + slot_g * kBTap, p.w_image + ((long long)cb * kTaps + tap) * kBTap, kBTap, full_g);
             }
             asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kC5GroupWarps * 32) : "memory");
             if (tr) trp[2] = clock64();
             if (AT) {
-                if (!(p.dbg & 1)) {
+                if (!(dbg & 1)) {
                     fence_after();                                       // (the slot's previous MMAs, observed through `empty`)
                     tmem_st32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + kTmemA + slot_g * 32, v);
                 }
                 fence_before();
             } else {
-                if (!(p.dbg & 1)) {
+                if (!(dbg & 1)) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) sts128(abd + i * 256, v[i].x, v[i].y, v[i].z, v[i].w);
                 }
-                if (!(p.dbg & 32)) fence_proxy_async();
+                if (!(dbg & 32)) fence_proxy_async();
             }
             if (tr) trp[3] = clock64();
             asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kC5GroupWarps * 32) : "memory");
             if (gt == 0) {
-                if (p.dbg & 4) mbar_arrive_a(full_g);
+                if (dbg & 4) mbar_arrive_a(full_g);
                 else mbar_arrive_expect_tx_a(full_g, kBTap);
             }
             if (tr) trp[4] = clock64();
@@ -564,7 +572,7 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
         for (int ph = 0; ph < n_phases; ++ph) {
             // the buffer held phase ph - 2: every copy warp has left it
             if (ph >= 2) {
-                if (lt == 0) wait_bar(ufree + 8 * (ph & 1), ((ph - 2) >> 1) & 1);
+                if (warp == kC5LoadWarp) wait_bar(ufree + 8 * (ph & 1), ((ph - 2) >> 1) & 1);   // (the whole warp: see the copy groups)
                 asm volatile("bar.sync %0, %1;" ::"n"(kC5Slots + 1), "n"(kC5LoadThreads) : "memory");
             }
             const int t = t_begin + k;
@@ -578,7 +586,7 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
             const int n = min(__ldg(p.n_uniq + t), kUmax);
             const int* up = p.uniq + (long long)t * kUmax;
             const uint8_t* src = p.in16 + cb * kURow + c8 * 16;
-            if (!(p.dbg & 8)) {
+            if (!(dbg & 8)) {
                 for (int j0 = r0; j0 < n; j0 += 8 * 8) {                 // 8 rows in flight per thread
                     int rows[8];
 #pragma unroll
@@ -622,7 +630,7 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
                 for (int s = NI == 2 ? ((G0 + me) & 1) : 0; s < per_tile; s += NI) {   // two issuers: stages with (G0 + s) % 2 == me
                     const int G = G0 + s;
                     const int slot_i = G & (NS - 1);
-                    const bool tr = p.trace != nullptr && blockIdx.x == 0 && G < 256 && lane == 0;
+                    const bool tr = DBG && p.trace != nullptr && blockIdx.x == 0 && G < 256 && lane == 0;
                     if (tr) p.trace[G * 8 + 5] = clock64();
                     // (every lane polls: a lane-0 poll followed by __syncwarp() cost ~1000 cycles per stage)
                     wait_bar(full + 8 * slot_i, (uint32_t)(G / NS) & 1);
@@ -632,7 +640,7 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
                     const int g0 = n_main == 1 ? 0 : ((2 * s) * n_main) / p.steps_total;         // main accumulator of the K steps
                     const int g1 = n_main == 1 ? 0 : ((2 * s + 1) * n_main) / p.steps_total;
                     if (elect_one()) {
-                        if (!(p.dbg & 2)) {
+                        if (!(dbg & 2)) {
 #pragma unroll
                             for (int j = 0; j < 2; ++j) {
                                 const int g = j == 0 ? g0 : g1;
@@ -672,9 +680,9 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
         for (int k = 0; k < n_my; ++k) {
             const int t = t_begin + k;
             const int row = __ldg(p.tile_rows + (long long)t * TM + q * 32 + lane);
-            const bool tre = p.trace != nullptr && blockIdx.x == 0 && q == 0 && lane == 0 && k < 64;
+            const bool tre = DBG && p.trace != nullptr && blockIdx.x == 0 && q == 0 && lane == 0 && k < 64;
             if (tre) p.trace[2048 + 4 * k] = clock64();
-            if (lane == 0) wait_bar(acc_full + 8 * acc, pacc);
+            wait_bar(acc_full + 8 * acc, pacc);                              // (every lane polls: no diverged warp in front of the .aligned loads)
             __syncwarp();
             fence_after();
             if (tre) p.trace[2048 + 4 * k + 1] = clock64();
@@ -712,7 +720,7 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
                         for (int j = 0; j < 16; ++j) sum[j] += __uint_as_float(v[j]);
                     }
                 }
-                if (p.dbg & 16) continue;
+                if (dbg & 16) continue;
                 // bias + activation + max|y|: chunk-uniform branches only (a per-element switch / bound test version spent
                 // ~5.5k cycles per tile here -- longer than the tensor-memory reads)
                 float y[16];
@@ -744,7 +752,7 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
                     y_max = fmaxf(y_max, m);
                 }
                 if (AT) {                                                    // stage the row; it leaves by bulk copy after the release
-                    if (p.dbg & 64) continue;
+                    if (dbg & 64) continue;
 #pragma unroll
                     for (int j = 0; j < 16; j += 4)
                         sts128(stage_row + (c0 + j) * 4, __float_as_uint(y[j]), __float_as_uint(y[j + 1]), __float_as_uint(y[j + 2]),
@@ -766,7 +774,7 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
             __syncwarp();
             if (lane == 0) mbar_arrive_a(acc_empty + 8 * acc);
             if (tre) p.trace[2048 + 4 * k + 3] = clock64();
-            if (AT && !(p.dbg & (16 | 128))) {                                   // the accumulators are free again; the row leaves asynchronously
+            if (AT && !(dbg & (16 | 128))) {                                   // the accumulators are free again; the row leaves asynchronously
                 fence_proxy_async();
                 if (row >= 0)
                     bulk_store(p.out + (long long)row * p.ld_out, a_base + (uint32_t)(q * 32 + lane) * kOutPitch, (uint32_t)p.c_out * 4u);
@@ -956,8 +964,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad5_kernel(const Wgrad5Args p)
                     for (int i = 0; i < 8; ++i) v[i] = lds128(ub + slot[i] * kURow);
                     // MMAs of stage s - 2 are complete once the stage buffer is free.  s == 1: the previous tile's last stage
                     // (h = 1, mt = 3) is done -> the dz half-1 buffer may be refilled; s == 5: half 0 of this tile is done.
-                    if (lane == 0) wait_bar(empty + 8 * stage, phase_bit ^ 1);
-                    __syncwarp();
+                    wait_bar(empty + 8 * stage, phase_bit ^ 1);                  // (every lane polls: a lane-0 wait leaves the warp diverged)
 #pragma unroll
                     for (int i = 0; i < 8; ++i) sts128(abd + (i >> 1) * (4 * kW_SBO) + (i & 1) * 512, v[i].x, v[i].y, v[i].z, v[i].w);
                     if (has_next) {
@@ -1083,10 +1090,12 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad5_kernel(const Wgrad5Args p)
 void set_attrs() {
     static bool done = false;
     if (done) return;
-    cudaFuncSetAttribute(conv5_kernel<15, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    cudaFuncSetAttribute(conv5_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    cudaFuncSetAttribute(conv5_kernel<15, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    cudaFuncSetAttribute(conv5_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(conv5_kernel<15, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(conv5_kernel<16, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(conv5_kernel<15, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(conv5_kernel<16, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(conv5_kernel<15, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(conv5_kernel<15, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     cudaFuncSetAttribute(wgrad5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmem);
     done = true;
 }
@@ -1183,12 +1192,16 @@ int hpl_conv5(const void* x16, const void* plan, int64_t n_out_rows, int64_t fil
     static int at_knob = -1;                                 // A operand from tensor memory (default) / HPL_CONV5_TMEM=0: shared memory
     if (at_knob < 0) { const char* e = getenv("HPL_CONV5_TMEM"); at_knob = e ? atoi(e) : 1; }
     const bool rows_ok = ld_out % 4 == 0 && c_out % 4 == 0;   // (bulk row stores: 16-byte multiples)
-    if (at_knob && a.n_main == 1 && rows_ok) {
-        if (filter_size == 15) conv5_kernel<15, true><<<grid, kC5Threads, kSmem, s>>>(a);
-        else conv5_kernel<16, true><<<grid, kC5Threads, kSmem, s>>>(a);
+    const bool at = at_knob && a.n_main == 1 && rows_ok;
+    if ((a.dbg != 0 || a.trace != nullptr) && filter_size == 15) {           // experiment hooks (tools/try_conv5_*.py)
+        if (at) conv5_kernel<15, true, true><<<grid, kC5Threads, kSmem, s>>>(a);
+        else conv5_kernel<15, false, true><<<grid, kC5Threads, kSmem, s>>>(a);
+    } else if (at) {
+        if (filter_size == 15) conv5_kernel<15, true, false><<<grid, kC5Threads, kSmem, s>>>(a);
+        else conv5_kernel<16, true, false><<<grid, kC5Threads, kSmem, s>>>(a);
     } else {
-        if (filter_size == 15) conv5_kernel<15, false><<<grid, kC5Threads, kSmem, s>>>(a);
-        else conv5_kernel<16, false><<<grid, kC5Threads, kSmem, s>>>(a);
+        if (filter_size == 15) conv5_kernel<15, false, false><<<grid, kC5Threads, kSmem, s>>>(a);
+        else conv5_kernel<16, false, false><<<grid, kC5Threads, kSmem, s>>>(a);
     }
     HPL_RETURN_LAST();
 }

@@ -271,12 +271,13 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
                 // warps, named barrier in between -- the SM serialises mbarrier operations (~40 cycles each; measured +4-5 %
                 // on the 580 -> 1024 and 324 -> 256 layers).  With 8 warps and three CTAs per SM the lock step costs more than
                 // it saves (cfg2: 0.211 -> 0.229 ms), so those keep per-warp waits / arrivals.
+                // (waits are executed by whole warps: a single waiting lane leaves its warp diverged in front of the barrier /
+                // the stores, which costs a slow reconvergence and dead-locked a sibling kernel in one build)
                 if (kGroupSync) {
-                    if (threadIdx.x == 0) mbar_wait_a(empty_a + 8 * stage, phase ^ 1);
+                    if (warp == 0) mbar_wait_a(empty_a + 8 * stage, phase ^ 1);
                     asm volatile("bar.sync 1, %0;" ::"n"(PW * 32) : "memory");
                 } else {
-                    if (lane0) mbar_wait_a(empty_a + 8 * stage, phase ^ 1);
-                    __syncwarp();
+                    mbar_wait_a(empty_a + 8 * stage, phase ^ 1);
                 }
                 const uint32_t a_hi = smem_base + stage * kStageBytes;
 #pragma unroll
@@ -614,8 +615,7 @@ wgrad_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_r
 #pragma unroll
             for (int d = 0; d < kPrefetch; ++d) {
                 if (kb0 + d >= n_kb) break;
-                if (lane0) mbar_wait_a(empty_a + 8 * stage, phase ^ 1);
-                __syncwarp();
+                mbar_wait_a(empty_a + 8 * stage, phase ^ 1);                        // (whole warp: see the forward kernel)
                 const uint32_t a_hi = smem_base + stage * kWStageBytes;
                 const uint32_t b_hi = a_hi + 2 * kWAHalf;
                 // convert and store one chunk at a time (keeps the live registers low: this kernel holds

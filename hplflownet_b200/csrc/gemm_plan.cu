@@ -63,7 +63,8 @@ constexpr int kC5Threads = 24 * 32;
 constexpr int kC5UIters = (kUmax * 8 + kC5CopyThreads - 1) / kC5CopyThreads;   // 8 row-chunk copies per thread and phase
 constexpr int kC5RingBytes = kC5Slots * (kATap + kBTap) > kC5OutStage + kC5SlotsT * kBTap ? kC5Slots * (kATap + kBTap)
                                                                                           : kC5OutStage + kC5SlotsT * kBTap;
-constexpr int kSmem = 2 * kUBuf + kC5RingBytes + 2 * kIdxBuf + 1024;
+constexpr int kC5UniqBuf = 2048;                 // a tile's list of distinct rows (kUmax ints), staged one tile ahead
+constexpr int kSmem = 2 * kUBuf + kC5RingBytes + 2 * kIdxBuf + kC5UniqBuf + 1024;
 constexpr int kUIters = (kUmax * 8 + kCopyThreads - 1) / kCopyThreads;      // 15 row-chunk copies per thread and phase
 constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
 static_assert(kSmem <= 232448, "shared memory budget");
@@ -142,6 +143,11 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
@@ -397,11 +403,19 @@ struct Conv5Args {
 // as soon as they are in registers / shared memory.
 // DBG: the instantiation with the experiment hooks (HPL_CONV5_DBG ablation bits, HPL_CONV5_TRACE clock stamps); the
 // production instantiation carries neither their tests nor their address arithmetic.
-template <int F, bool AT, bool DBG>
+// TPS: taps per stage (tensor-memory path only: 2).  The per-stage costs that do not scale with the data -- the issuer's
+// barrier poll / fence / commit (~400 cycles per stage on one thread, which paced the one-tap version), the groups'
+// empty wait and two named barriers -- are then paid once per TWO taps; a phase of F = 15 taps is 7 double stages and one
+// single stage.
+template <int F, bool AT, bool DBG, int TPS>
 __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p) {
+    static_assert(TPS == 1 || (AT && TPS == 2), "two-tap stages exist on the tensor-memory path only");
     const int dbg = DBG ? p.dbg : 0;
     extern __shared__ uint8_t smem_raw[];
-    constexpr int NS = AT ? kC5SlotsT : kC5Slots;                        // ring slots (group g fills slots g, g + 4, ...)
+    constexpr int SP = (F + TPS - 1) / TPS;                              // stages per phase
+    constexpr int NS = AT ? kC5SlotsT / TPS : kC5Slots;                  // ring slots (group g fills slots g, g + 4, ...)
+    constexpr uint32_t kBSlot = kBTap * TPS;                             // weight tiles of one stage
+    constexpr uint32_t kASlotCols = 32 * TPS;                            // TMEM columns of one A slot
     __shared__ __align__(8) uint64_t bars[2 * kC5SlotsT + 4 + 4];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float bias_s[64];                           // bias (zero beyond c_out / without one)
@@ -422,13 +436,13 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
     const int n_my = max(0, t_end - t_begin);
     const int CB = p.cb_count;
     const int n_phases = n_my * CB;
-    const int n_stages = n_phases * F;
+    const int n_stages = n_phases * SP;
     // MMA issuers: two on the shared-memory A path (alternate stages, own accumulators); ONE on the tensor-memory path, whose
     // accumulators (128 columns per tile) are then double-buffered next to the A slots, so the epilogue of a tile
     // overlaps the next tile's stages.
     constexpr int NI = AT ? 1 : 2;
     const int acc_cols = NI * p.n_main * 128;                            // TMEM columns of one tile: issuers x n_main x [main | cross]
-    const int acc_stages = (2 * acc_cols + (AT ? kC5SlotsT * 32 : 0) <= 512) ? 2 : 1;
+    const int acc_stages = (2 * acc_cols + (AT ? NS * (int)kASlotCols : 0) <= 512) ? 2 : 1;
     constexpr uint32_t kTmemA = 256;                                     // AT: first column of the A slots (32 columns each)
     constexpr uint32_t kOutPitch = 64 * 4 + 16;                          // AT: staged output row (272 B: odd multiple of 16 -> conflict-free)
 
@@ -485,13 +499,15 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
                     if (++cb == CB) { cb = 0; ++k; }
                 }
                 ++ph;
-                next_ph_tap0 += F;
+                next_ph_tap0 += SP;
                 if (lead_warp) wait_bar(ufull + 8 * (ph & 1), (ph >> 1) & 1);
                 asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kC5GroupWarps * 32) : "memory");
                 ub = u_base + (ph & 1) * kUBuf + src_off;
                 ibs = idx_base + (k & 1) * kIdxBuf + idx_off;
             }
-            const int tap = G - (next_ph_tap0 - F);
+            const int tap = (G - (next_ph_tap0 - SP)) * TPS;                 // (first) tap of the stage
+            const bool two = TPS == 2 && tap + 1 < F;                        // F odd: the phase's last stage holds one tap
+            const uint32_t w_bytes = two ? 2 * kBTap : kBTap;
             const int slot_g = G & (NS - 1);                                 // (NS == 4: always grp)
             const uint32_t full_g = full + 8 * slot_g, empty_g = empty + 8 * slot_g;
             const uint32_t par_g = (uint32_t)(G / NS) & 1;
@@ -534,14 +550,30 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
                 // the stage's weight tile (8 KB, one bulk copy) is requested by the group itself as soon as the slot is free
                 // (its complete_tx may land before the expect_tx below: the transaction count may go negative meanwhile)
                 if (!(dbg & 4) && elect_one())
-                    bulk_load_a(b_base + slot_g * kBTap, p.w_image + ((long long)cb * kTaps + tap) * kBTap, kBTap, full_g);
+                    bulk_load_a(b_base + slot_g * kBSlot, p.w_image + ((long long)cb * kTaps + tap) * kBTap, w_bytes, full_g);
             }
             asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kC5GroupWarps * 32) : "memory");
             if (tr) trp[2] = clock64();
             if (AT) {
                 if (!(dbg & 1)) {
                     fence_after();                                       // (the slot's previous MMAs, observed through `empty`)
-                    tmem_st32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + kTmemA + slot_g * 32, v);
+                    const uint32_t ta = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + kTmemA + slot_g * kASlotCols;
+                    tmem_st32(ta, v);
+                    if (two) {                                           // second tap: read, un-rotate, store (the registers are free again)
+                        const uint32_t sl = lds_u16(idx_base + (k & 1) * kIdxBuf + ((tap + 1) * TM + gt) * 2);
+                        const uint32_t src = u_base + (ph & 1) * kUBuf + sl * kURow;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = lds128(src + (((i + lane) & 7) << 4));
+#pragma unroll
+                        for (int b = 1; b < 8; b <<= 1) {
+                            uint4 t[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) t[i] = (lane & b) ? v[(i - b) & 7] : v[i];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] = t[i];
+                        }
+                        tmem_st32(ta + 32, v);
+                    }
                 }
                 fence_before();
             } else {
@@ -555,7 +587,7 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
             asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kC5GroupWarps * 32) : "memory");
             if (gt == 0) {
                 if (dbg & 4) mbar_arrive_a(full_g);
-                else mbar_arrive_expect_tx_a(full_g, kBTap);
+                else mbar_arrive_expect_tx_a(full_g, w_bytes);
             }
             if (tr) trp[4] = clock64();
         }
@@ -568,6 +600,21 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
         const int lt = threadIdx.x - kC5LoadWarp * 32;                    // 0 .. 63
         const int c8 = lt & 7, r0 = lt >> 3;                              // chunk of the line; rows r0, r0 + 8, ...
         const long long row_bytes = (long long)CB * kURow;
+        // The tile's list of distinct rows is read from SHARED memory: it is fetched (cp.async) while the previous tile's
+        // last phase loads.  Read with __ldg at the point of use, the cold list cost one DRAM round trip per pass of 64
+        // rows -- 8 serialised round trips at every tile boundary, ~3500 idle cycles per tile for the whole CTA.
+        const uint32_t uq_base = idx_base + 2 * kIdxBuf;
+        auto fetch_list = [&](int t) {
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.uniq + (long long)t * kUmax);
+            for (int c = lt; c < kUmax * 4 / 16; c += kC5LoadThreads) cp_async16(uq_base + c * 16, src + c * 16);
+        };
+        int n_cur = 0, n_next = 0;
+        if (n_phases > 0) {
+            fetch_list(t_begin);
+            n_cur = min(__ldg(p.n_uniq + t_begin), kUmax);
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            asm volatile("bar.sync %0, %1;" ::"n"(kC5Slots + 1), "n"(kC5LoadThreads) : "memory");
+        }
         int k = 0, cb = 0;
         for (int ph = 0; ph < n_phases; ++ph) {
             // the buffer held phase ph - 2: every copy warp has left it
@@ -583,24 +630,28 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
                     cp_async16(idx_base + (k & 1) * kIdxBuf + (lt + i * kC5LoadThreads) * 16,
                                reinterpret_cast<const uint8_t*>(p.local) + ((long long)t * (kTaps * TM)) * 2 + (lt + i * kC5LoadThreads) * 16);
             }
-            const int n = min(__ldg(p.n_uniq + t), kUmax);
-            const int* up = p.uniq + (long long)t * kUmax;
+            const int n = n_cur;
             const uint8_t* src = p.in16 + cb * kURow + c8 * 16;
             if (!(dbg & 8)) {
                 for (int j0 = r0; j0 < n; j0 += 8 * 8) {                 // 8 rows in flight per thread
                     int rows[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) rows[i] = j0 + 8 * i < n ? __ldg(up + j0 + 8 * i) : -1;
+                    for (int i = 0; i < 8; ++i) rows[i] = j0 + 8 * i < n ? lds_s32(uq_base + (j0 + 8 * i) * 4) : -1;
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
                         if (rows[i] >= 0) cp_async16(ub + (j0 + 8 * i) * kURow, src + (long long)rows[i] * row_bytes);
                 }
             }
+            if (cb == CB - 1 && k + 1 < n_my) {                          // the tile's last phase: fetch the next tile's list
+                asm volatile("bar.sync %0, %1;" ::"n"(kC5Slots + 1), "n"(kC5LoadThreads) : "memory");   // (everyone has read this one)
+                fetch_list(t + 1);
+                n_next = min(__ldg(p.n_uniq + t + 1), kUmax);
+            }
             // one mbarrier arrival per phase (not one asynchronous arrival per thread): wait for the own copies, meet, arrive
             asm volatile("cp.async.wait_all;" ::: "memory");
             asm volatile("bar.sync %0, %1;" ::"n"(kC5Slots + 1), "n"(kC5LoadThreads) : "memory");
             if (lt == 0) mbar_arrive_a(ufull + 8 * (ph & 1));
-            if (++cb == CB) { cb = 0; ++k; }
+            if (++cb == CB) { cb = 0; ++k; n_cur = n_next; }
         }
     } else if (warp == kC5MmaWarp || (NI == 2 && warp == kC5MmaWarp + 1)) {
         // ------------------------------------------------------------------ MMA issuers
@@ -617,7 +668,7 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
             constexpr uint32_t kIdescLo = instr_desc(0, TM, 64, 0, 0);
             constexpr uint64_t kDescA = (uint64_t)((kA_LBO >> 4) & 0x3fff) << 16 | (uint64_t)(128 >> 4) << 32 | (uint64_t)1 << 46;
             constexpr uint64_t kDescB = (uint64_t)((kB_LBO >> 4) & 0x3fff) << 16 | (uint64_t)(128 >> 4) << 32 | (uint64_t)1 << 46;
-            const int per_tile = CB * F;
+            const int per_tile = CB * SP;
             const int n_main = AT ? 1 : p.n_main;
             int acc = 0;
             uint32_t pacc = 0;
@@ -636,7 +687,8 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
                     wait_bar(full + 8 * slot_i, (uint32_t)(G / NS) & 1);
                     fence_after();
                     if (tr) p.trace[G * 8 + 6] = clock64();
-                    const uint32_t a16 = (a_base + slot_i * kATap) >> 4, b16 = (b_base + slot_i * kBTap) >> 4;
+                    const uint32_t a16 = (a_base + slot_i * kATap) >> 4, b16 = (b_base + slot_i * kBSlot) >> 4;
+                    const int n_taps = (TPS == 2 && !(F % 2 == 1 && s % SP == SP - 1)) ? 2 : 1;
                     const int g0 = n_main == 1 ? 0 : ((2 * s) * n_main) / p.steps_total;         // main accumulator of the K steps
                     const int g1 = n_main == 1 ? 0 : ((2 * s + 1) * n_main) / p.steps_total;
                     if (elect_one()) {
@@ -648,9 +700,14 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
                                 const uint32_t bb = b16 + ((j * 2 * kB_LBO) >> 4);
                                 const uint32_t dg = d0 + (uint32_t)(g * 128);
                                 if (AT) {
-                                    const uint32_t at = tmem_d + kTmemA + (uint32_t)(slot_i * 32 + 8 * j);
+                                    const uint32_t at = tmem_d + kTmemA + (uint32_t)(slot_i * kASlotCols + 8 * j);
                                     umma_f16_ts(dg, at, kDescB | bb, kIdescMain, g == pg);                 // x_hi . [W_hi | W_lo]
                                     umma_f16_ts(dg + 64, at + 16, kDescB | bb, kIdescLo, 1);               // x_lo . W_hi
+                                    if (n_taps == 2) {                                                     // the stage's second tap
+                                        const uint32_t bb2 = bb + (kBTap >> 4);
+                                        umma_f16_ts(dg, at + 32, kDescB | bb2, kIdescMain, 1);
+                                        umma_f16_ts(dg + 64, at + 32 + 16, kDescB | bb2, kIdescLo, 1);
+                                    }
                                 } else {
                                     umma_f16(dg, kDescA | ah, kDescB | bb, kIdescMain, g == pg);           // x_hi . [W_hi | W_lo]
                                     umma_f16(dg + 64, kDescA | (ah + (kAPlane >> 4)), kDescB | bb, kIdescLo, 1);   // x_lo . W_hi
@@ -1044,7 +1101,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad5_kernel(const Wgrad5Args p)
         const int m = q * 32 + lane;                                              // M row of the tile: tap_l * 32 + channel
         const int ch = cb * 32 + (m & 31);
         for (int fl = 0; fl < n_flush; ++fl) {
-            if (lane == 0) wait_bar(accb, fl & 1);
+            wait_bar(accb, fl & 1);
             __syncwarp();
             fence_after();
 #pragma unroll 1
@@ -1090,12 +1147,15 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad5_kernel(const Wgrad5Args p)
 void set_attrs() {
     static bool done = false;
     if (done) return;
-    cudaFuncSetAttribute(conv5_kernel<15, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    cudaFuncSetAttribute(conv5_kernel<16, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    cudaFuncSetAttribute(conv5_kernel<15, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    cudaFuncSetAttribute(conv5_kernel<16, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    cudaFuncSetAttribute(conv5_kernel<15, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    cudaFuncSetAttribute(conv5_kernel<15, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(conv5_kernel<15, false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(conv5_kernel<16, false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(conv5_kernel<15, true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(conv5_kernel<16, true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(conv5_kernel<15, false, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(conv5_kernel<15, true, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(conv5_kernel<15, true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(conv5_kernel<16, true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(conv5_kernel<15, true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     cudaFuncSetAttribute(wgrad5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmem);
     done = true;
 }
@@ -1189,19 +1249,25 @@ int hpl_conv5(const void* x16, const void* plan, int64_t n_out_rows, int64_t fil
     a.trace = nullptr;
     { const char* e = getenv("HPL_CONV5_TRACE"); if (e) a.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0)); }
     const unsigned grid = (unsigned)(a.n_tiles < num_sms() ? a.n_tiles : num_sms());
-    static int at_knob = -1;                                 // A operand from tensor memory (default) / HPL_CONV5_TMEM=0: shared memory
-    if (at_knob < 0) { const char* e = getenv("HPL_CONV5_TMEM"); at_knob = e ? atoi(e) : 1; }
+    // A operand: HPL_CONV5_TMEM=0 shared memory; 1 tensor memory, one tap per stage; 2 (default) tensor memory, two taps per stage
+    static int at_knob = -1;
+    if (at_knob < 0) { const char* e = getenv("HPL_CONV5_TMEM"); at_knob = e ? atoi(e) : 2; }
     const bool rows_ok = ld_out % 4 == 0 && c_out % 4 == 0;   // (bulk row stores: 16-byte multiples)
     const bool at = at_knob && a.n_main == 1 && rows_ok;
-    if ((a.dbg != 0 || a.trace != nullptr) && filter_size == 15) {           // experiment hooks (tools/try_conv5_*.py)
-        if (at) conv5_kernel<15, true, true><<<grid, kC5Threads, kSmem, s>>>(a);
-        else conv5_kernel<15, false, true><<<grid, kC5Threads, kSmem, s>>>(a);
+    const bool hooks = (a.dbg != 0 || a.trace != nullptr) && filter_size == 15;   // experiment hooks (tools/try_conv5_*.py)
+    if (at && at_knob >= 2) {
+        if (hooks) conv5_kernel<15, true, true, 2><<<grid, kC5Threads, kSmem, s>>>(a);
+        else if (filter_size == 15) conv5_kernel<15, true, false, 2><<<grid, kC5Threads, kSmem, s>>>(a);
+        else conv5_kernel<16, true, false, 2><<<grid, kC5Threads, kSmem, s>>>(a);
+    } else if (hooks) {
+        if (at) conv5_kernel<15, true, true, 1><<<grid, kC5Threads, kSmem, s>>>(a);
+        else conv5_kernel<15, false, true, 1><<<grid, kC5Threads, kSmem, s>>>(a);
     } else if (at) {
-        if (filter_size == 15) conv5_kernel<15, true, false><<<grid, kC5Threads, kSmem, s>>>(a);
-        else conv5_kernel<16, true, false><<<grid, kC5Threads, kSmem, s>>>(a);
+        if (filter_size == 15) conv5_kernel<15, true, false, 1><<<grid, kC5Threads, kSmem, s>>>(a);
+        else conv5_kernel<16, true, false, 1><<<grid, kC5Threads, kSmem, s>>>(a);
     } else {
-        if (filter_size == 15) conv5_kernel<15, false, false><<<grid, kC5Threads, kSmem, s>>>(a);
-        else conv5_kernel<16, false, false><<<grid, kC5Threads, kSmem, s>>>(a);
+        if (filter_size == 15) conv5_kernel<15, false, false, 1><<<grid, kC5Threads, kSmem, s>>>(a);
+        else conv5_kernel<16, false, false, 1><<<grid, kC5Threads, kSmem, s>>>(a);
     }
     HPL_RETURN_LAST();
 }

@@ -886,6 +886,7 @@ struct Wgrad5Args {
     const uint32_t* x_amax;
     const uint32_t* dz_amax;
     int n_tiles, cb_count, cbo_count, filter_size, c_in, c_out, tiles_per_cta;
+    int dbg;                      // timing experiments (HPL_WGRAD5_DBG): 1 no fence.proxy.async, 4 no MMAs, 8 no operand stores
 };
 
 __global__ void __launch_bounds__(kThreads, 1) wgrad5_kernel(const Wgrad5Args p) {
@@ -1023,7 +1024,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad5_kernel(const Wgrad5Args p)
                     // (h = 1, mt = 3) is done -> the dz half-1 buffer may be refilled; s == 5: half 0 of this tile is done.
                     wait_bar(empty + 8 * stage, phase_bit ^ 1);                  // (every lane polls: a lane-0 wait leaves the warp diverged)
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) sts128(abd + (i >> 1) * (4 * kW_SBO) + (i & 1) * 512, v[i].x, v[i].y, v[i].z, v[i].w);
+                    for (int i = 0; i < 8; ++i)
+                        if (!(p.dbg & 8)) sts128(abd + (i >> 1) * (4 * kW_SBO) + (i & 1) * 512, v[i].x, v[i].y, v[i].z, v[i].w);
                     if (has_next) {
                         if (s < 4) {                                              // next tile's x rows
                             if (s == 0) load_idx_block(k + 1);
@@ -1036,12 +1038,12 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad5_kernel(const Wgrad5Args p)
                             cp_async_arrive_noinc(bfull);
                         }
                     }
-                    if (s == 1 && k > 0) {                                        // previous tile's stage 7 (last user of half 1) has completed
+                    if (s == 1 && k > 0) {                        // previous tile's stage 7 (last user of half 1) has completed
                         load_dz_half(k, 1, b_base + kWBHalf);
                         cp_async_arrive_noinc(bfull + 8);
                     }
                     if (mt == 0) wait_bar(bfull + 8 * h, k & 1);                  // this half's dz rows have landed
-                    fence_proxy_async();
+                    if (!(p.dbg & 1)) fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_a(full + 8 * stage);
                     if (++stage == 2) { stage = 0; phase_bit ^= 1; }
@@ -1075,6 +1077,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad5_kernel(const Wgrad5Args p)
                         if (elect_one()) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
+                                if (p.dbg & 4) break;
                                 const uint32_t acc = (since_flush | h | j) != 0;
                                 umma_f16(d, kDesc | (a16 + j * 16), kDesc | (b16 + j * 16), kIdescMain, acc);
                                 umma_f16(d + 64, kDesc | (a16 + (kWPlane >> 4) + j * 16), kDesc | (b16 + j * 16), kIdescLo, 1);
@@ -1293,6 +1296,7 @@ int hpl_wgrad5(const void* x16, const void* dz16, const void* plan, int64_t n_ou
     a.n_tiles = (int)hpl_plan_tiles(n_out_rows);
     a.cb_count = cb_of(c_in); a.cbo_count = cb_of(c_out);
     a.filter_size = (int)filter_size; a.c_in = (int)c_in; a.c_out = (int)c_out;
+    { const char* e = getenv("HPL_WGRAD5_DBG"); a.dbg = e ? atoi(e) : 0; }
     int ranges = num_sms() / a.cb_count;
     if (ranges < 1) ranges = 1;
     if (ranges > a.n_tiles) ranges = a.n_tiles;

@@ -156,6 +156,21 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     return v;
 }
 
+
+// Un-rotate the eight 16-byte chunks a copy thread read in lane-rotated order (v[i] = chunk (i + lane) % 8): a barrel of
+// three conditional rotations, 96 SEL.  (Selecting arithmetically on the FMA pipe -- a * m + b * (1 - m), two IMADs -- for
+// one of the stages was slower, 0.0961 -> 0.0996 ms: the copy warps are bound by issue slots, not by the ALU pipe.)
+__device__ __forceinline__ void unrotate8(uint4* v, int lane) {
+#pragma unroll
+    for (int b = 1; b < 8; b <<= 1) {
+        uint4 t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = (lane & b) ? v[(i - b) & 7] : v[i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = t[i];
+    }
+}
+
 // tcgen05.mma with the A operand in tensor memory (M = 128: lane = row, every 32-bit column = two consecutive K elements)
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -523,14 +538,7 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
                     const uint32_t src = u_base + (ph & 1) * kUBuf + sl * kURow;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = lds128(src + (((i + lane) & 7) << 4));
-#pragma unroll
-                    for (int b = 1; b < 8; b <<= 1) {                      // v[i] holds chunk (i + lane) % 8: rotate by the set bits of lane % 8
-                        uint4 t[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) t[i] = (lane & b) ? v[(i - b) & 7] : v[i];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = t[i];
-                    }
+                    unrotate8(v, lane);                                  // v[i] held chunk (i + lane) % 8
                 }
             } else if (!(dbg & 1)) {
 #pragma unroll
@@ -564,14 +572,7 @@ __global__ void __launch_bounds__(kC5Threads, 1) conv5_kernel(const Conv5Args p)
                         const uint32_t src = u_base + (ph & 1) * kUBuf + sl * kURow;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) v[i] = lds128(src + (((i + lane) & 7) << 4));
-#pragma unroll
-                        for (int b = 1; b < 8; b <<= 1) {
-                            uint4 t[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) t[i] = (lane & b) ? v[(i - b) & 7] : v[i];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] = t[i];
-                        }
+                        unrotate8(v, lane);
                         tmem_st32(ta + 32, v);
                     }
                 }

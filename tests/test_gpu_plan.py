@@ -146,3 +146,35 @@ def test_engine5_many_tiles_per_sm_and_fused_normalisation():
     dw = ops.wgrad5(x16, ops.h16b_split(dz, 64, dz_amax), plan, 64, 64, bound, dz_amax)
     xd = torch.cat((xn.double(), torch.zeros(1, 64, dtype=torch.float64, device=DEV)), 0)
     assert_close(dw, torch.einsum("fvc,vo->fco", xd[nbr.long()], dz.double()), "weight gradient, 8 clouds")
+
+
+_VARIANT_SCRIPT = r"""
+import torch
+from hplflownet_b200 import ops, plans
+from tests.test_gpu_plan import _table
+from tests.test_gpu_gemm import _reference
+from tests._util import assert_close
+nbr = _table(8192, 5, clouds=4)
+plan = plans.build(nbr)
+torch.manual_seed(1)
+x = torch.randn(nbr.size(1), 64, device="cuda") * 1.7
+w = torch.randn(15, 64, 64, device="cuda") * 0.03
+b = torch.randn(64, device="cuda")
+amax = ops.absmax(x)
+y = ops.conv5(ops.h16b_split(x, 64, amax), plan, 64, w, b, ops.ACT_LEAKY, amax)
+assert_close(y, _reference(x, nbr, w, b, ops.ACT_LEAKY), "engine 5 variant")
+print("variant ok")
+"""
+
+
+@pytest.mark.parametrize("knob", ["0", "1", "2"])
+def test_engine5_operand_paths(knob):
+    """The three builds of the forward kernel -- A operand in shared memory (0), in tensor memory with one-tap (1) or
+    two-tap (2, default) stages -- on a table with several tiles per CTA.  The knob is read once per process."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, HPL_CONV5_TMEM=knob)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "variant ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

@@ -19,7 +19,9 @@ RELAX_MAX = 4096
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    # raw handle of the current stream of the current device (torch.cuda.current_stream() builds a Stream object through
+    # several Python layers: ~12 us per call, 270 calls per model forward)
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def _tap_offsets(filter_size, device):

@@ -1,26 +1,24 @@
-// Engine 5: the lattice convolution (blur forward / data gradient, models/bilateralNN.py:198-221) as a persistent
-// tcgen05 kernel that loads every DISTINCT neighbour row of a 128-vertex tile ONCE.
+// Engine 5: the lattice convolution (blur forward / data gradient, models/bilateralNN.py:198-221) and its weight gradient
+// as persistent tcgen05 kernels that load every DISTINCT neighbour row of a 128-vertex tile ONCE.
 //
 // Engines 2 / 4 gather F = 15 rows per vertex straight from L2 (1.2 GB of L2 -> SM traffic per cfg2 x 32 launch, the
 // measured floor of those designs).  Here a per-lattice tile plan (plan.cu) lists, for every tile of 128 spatially
-// coherent vertices, the ~320 distinct rows its 15 x 128 table entries reference; the kernel
-//   1. stages those rows once in shared memory (cp.async, one 128-byte line per quarter warp, double-buffered: the
-//      next phase's rows arrive while the current phase computes),
-//   2. builds the UMMA A operand of every tap by shared -> shared copies (LDS.128 / STS.128, conflict-free on both
-//      sides: a quarter warp moves one staged row into 8 different bank groups of the K-major no-swizzle layout),
+// coherent vertices, the ~320 distinct rows its 15 x 128 table entries reference; conv5_kernel
+//   1. stages those rows once in shared memory (loader warps, cp.async, one 128-byte line per quarter warp,
+//      double-buffered: the next phase's rows arrive while the current phase computes),
+//   2. builds the UMMA A operand of every tap from the staged rows -- in TENSOR MEMORY (tcgen05.st by the thread that owns
+//      the tile row; default) or, for wide K / odd widths, in shared memory (LDS.128 / STS.128, conflict-free on both sides),
 //   3. runs 3xFP16 as TWO MMAs per K step instead of three: the weight tile holds [W_hi ; W_lo] as 128 N rows, so
 //      x_hi . [W_hi | W_lo] is one M128 N128 K16 instruction (main term in columns 0-63, cross term in 64-127) and
-//      x_lo . W_hi (N = 64) accumulates onto the cross columns.  The A operand is read from shared memory once for two
-//      products (the SM's 128 B / clk shared-memory port is the binding resource of this kernel).
+//      x_lo . W_hi (N = 64) accumulates onto the cross columns.
 // Operands arrive pre-split ("h16b" image: per row and 32-channel block, 32 fp16 hi | 32 fp16 lo = one 128-byte line;
 // x / s = hi + lo * 2^-11, s a per-tensor power of two, see gemm_tc16.cu); producers of lattice rows write that image
 // directly (rows.cu), so nothing is converted here.
 //
-// Work decomposition: CTA = one SM, contiguous range of tiles; phase = (tile, 32-channel block); stage = two taps of a
-// phase (A: 2 x 16.1 KB, W: 2 x 8 KB), ring of 2.  Warps: 0-7 copy (U loads + A stage copies), 8 MMA issuer (one
-// thread), 9 weight stream (cp.async.bulk, one 16 KB copy per stage), 10-13 epilogue (tcgen05.ld, bias, activation,
-// fp32 row stores in the reference's vertex order, max|out| statistic) overlapped with the next tile through
-// double-buffered TMEM accumulators.
+// Work decomposition of conv5_kernel: CTA = one SM, contiguous range of tiles; phase = (tile, 32-channel block); stage =
+// one or two taps of a phase.  Warps: 0-15 four copy groups, 16 (17) MMA issuer(s), 18-19 row loaders, 20-23 epilogue
+// (tcgen05.ld, bias, activation, fp32 rows in the reference's vertex order, max|out| statistic), overlapped with the next
+// tile through double-buffered TMEM accumulators.  Details at the kernel; measurements in DESIGN.md 3.2c.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -41,26 +39,22 @@ constexpr int kUBuf = (kUmax + 1) * kURow;       // + the zero row (slot kUmax)
 constexpr uint32_t kA_LBO = TM * 16 + 16;        // 2064: K-chunk stride of an A plane (129 x 16 B: odd -> conflict-free)
 constexpr int kAPlane = 4 * kA_LBO;              // 8256: hi (or lo) plane of one tap, 32 channels
 constexpr int kATap = 2 * kAPlane;               // 16512
-constexpr int kAStage = 2 * kATap;               // two taps
 constexpr uint32_t kB_LBO = 128 * 16;            // weight tile: 128 N rows ([W_hi ; W_lo]) x 32 K
 constexpr int kBTap = 4 * kB_LBO;                // 8192
-constexpr int kBStage = 2 * kBTap;
-constexpr int kStages = 2;
 constexpr int kC5Slots = 4;                      // forward kernel: ring of one-tap stages (shared-memory A path) = number of copy groups
 constexpr int kC5SlotsT = 8;                     // ring on the tensor-memory A path (A slots in TMEM, 8 weight tiles in shared memory)
 constexpr int kC5OutStage = 128 * (64 * 4 + 16); // tensor-memory A path: staged output tile (272-byte rows)
 constexpr int kIdxBuf = kTaps * TM * 2;          // 4096 B of uint16 slots
 constexpr int kCopyWarps = 8, kCopyThreads = kCopyWarps * 32;      // weight-gradient kernel: one copy group
-constexpr int kMmaWarp = 8, kWWarp = 9;
+constexpr int kMmaWarp = 8;
 constexpr int kThreads = 14 * 32;
-// forward kernel: TWO copy groups of 8 warps, group g fills ring slot g (alternate stages), so one group's fixed latencies
-// (barrier wake-up, proxy fence) overlap the other group's shared-memory traffic
-constexpr int kC5CopyWarps = 16, kC5CopyThreads = kC5CopyWarps * 32;
+// forward kernel: FOUR copy groups of 4 warps; group g builds the stages with G % 4 == g, so one group's fixed latencies
+// (barrier wake-up, named barriers, fences) overlap the other groups' work
+constexpr int kC5CopyWarps = 16;
 constexpr int kC5GroupWarps = kC5CopyWarps / 4;                     // four copy groups of four warps: group g fills ring slot g
 constexpr int kC5MmaWarp = 16, kC5LoadWarp = 18, kC5LoadWarps = 2;  // warps 16, 17: MMA issuers; 18, 19: row loaders; 20-23: epilogue
 constexpr int kC5LoadThreads = kC5LoadWarps * 32;
 constexpr int kC5Threads = 24 * 32;
-constexpr int kC5UIters = (kUmax * 8 + kC5CopyThreads - 1) / kC5CopyThreads;   // 8 row-chunk copies per thread and phase
 constexpr int kC5RingBytes = kC5Slots * (kATap + kBTap) > kC5OutStage + kC5SlotsT * kBTap ? kC5Slots * (kATap + kBTap)
                                                                                           : kC5OutStage + kC5SlotsT * kBTap;
 constexpr int kC5UniqBuf = 2048;                 // a tile's list of distinct rows (kUmax ints), staged one tile ahead
@@ -102,30 +96,6 @@ __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity), "r"(0x100000u)
             : "memory");
         if (!done && tries >= 64) {
-            unsigned long long now;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000ull) __trap();
-        }
-    }
-}
-
-// polling wait for the two MMA-issuing threads (alone in their warps): test_wait returns at once, so the issuer reacts
-// within one poll instead of a suspend / wake-up round trip
-__device__ __forceinline__ void wait_bar_poll(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    unsigned long long t0 = 0;
-    for (uint32_t tries = 0; !done; ++tries) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (!done && (tries & 0xffff) == 0xffff) {
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
             if (t0 == 0) t0 = now;
@@ -403,19 +373,20 @@ struct Conv5Args {
 
 // F = taps processed (15: HPLFlowNet's r = 1 neighbourhood; 16: any other count, padded with zero taps)
 //
-// Pipeline.  A stage is ONE tap of one phase (A: 16.1 KB hi | lo planes, W: 8 KB), ring of kC5Slots = 4.  The stages of a
-// CTA are numbered G = 0, 1, 2, ... across phases and tiles (phase = G / F, tap = G % F, slot = G % 4); copy group g
-// (8 warps) fills the stages with G % 2 == g, i.e. it owns slots g and g + 2 and always has a second stage to work on
-// while the tensor core drains the first.  Measured on the previous structure (two-tap stages, ring of 2): a slot's
-// copy -> MMA -> copy chain carries ~1750 cycles of hand-over latency per round trip, so per-stage time was
-// latency + copy + MMA, not their maximum; four slots in flight hide it.
-// AT: the A operand lives in TENSOR MEMORY: every copy thread owns one row of the tile, reads its staged row from shared
-// memory (chunk order rotated by the lane so that a quarter warp hits 8 different bank groups, un-rotated in registers) and
-// writes it with tcgen05.st; the MMA then fetches only the weight tile from shared memory (71 -> 39 KB of shared-memory
-// traffic per tap-stage).  The shared memory the A stages no longer need stages the output tile, which leaves through the
-// bulk-copy engine (one 256-byte row per instruction) instead of 32-lines-per-instruction LSU stores.  Tensor memory:
-// accumulators [0, 256), A slots [256, 384): the accumulators are single-buffered in this mode, so the epilogue frees them
-// as soon as they are in registers / shared memory.
+// Pipeline.  The stages of a CTA are numbered G = 0, 1, 2, ... across phases and tiles; copy group g (4 warps) builds the
+// stages with G % 4 == g, the ring has NS slots (slot = G % NS).  Measured on earlier structures: a slot's
+// copy -> MMA -> copy chain carries ~1750 cycles of hand-over latency per round trip (so the ring must be deep enough to
+// hide it), the SM serialises mbarrier operations (so there is ONE wait and ONE arrival per group and stage, executed by
+// the group's whole first warp / one thread, with named barriers inside the group), and a warp must never wait with a
+// single lane in front of a named barrier (see the copy loop).
+// AT = false (shared-memory A path; wide K with n_main > 1, odd c_out): a stage is one tap (A: 16.1 KB hi | lo planes in
+// the K-major no-swizzle UMMA layout, W: 8 KB), NS = 4, two MMA issuers on alternate stages with their own accumulators.
+// AT = true (default): the A operand lives in TENSOR MEMORY.  Every copy thread owns one row of the tile, reads its staged
+// line from shared memory (chunk order rotated by the lane so that a quarter warp hits 8 different bank groups,
+// un-rotated in registers) and writes it with tcgen05.st; the MMA then fetches only the weight tile from shared memory
+// (71 -> 39 KB of shared-memory traffic per tap).  The shared memory the A stages no longer need stages the output tile,
+// which leaves through the bulk-copy engine (one 256-byte row per instruction) instead of 32-lines-per-instruction LSU
+// stores.  One issuer; tensor memory: accumulators 2 x 128 columns (double-buffered), A slots NS x 32 * TPS columns.
 // DBG: the instantiation with the experiment hooks (HPL_CONV5_DBG ablation bits, HPL_CONV5_TRACE clock stamps); the
 // production instantiation carries neither their tests nor their address arithmetic.
 // TPS: taps per stage (tensor-memory path only: 2).  The per-stage costs that do not scale with the data -- the issuer's

@@ -161,7 +161,12 @@ __global__ void weight_image16_kernel(const float* __restrict__ w, long long w_s
 // PW producer warps (8: two CTAs per SM; 16: the 256-wide tile, one CTA per SM).  kb_per_split > 0: the K blocks are
 // split over blockIdx.z, every CTA accumulates its range and adds its partial tile to `out` with fp32 RED (out zeroed
 // by the launcher, bias / activation applied by bias_act_kernel afterwards).
-template <bool I64, int TNv, int kStagesV, int PW, int PF = 3>
+// CL = 2 (256-wide tile only): the two CTAs of a thread-block cluster work on adjacent M tiles of the same (N tile, K
+// range) and SHARE the weight stream -- each loads one half of a stage's weight tile and multicasts it into both CTAs
+// (cp.async.bulk ... .multicast::cluster); a stage slot is free again when BOTH CTAs' MMAs on it have completed
+// (tcgen05.commit ... .multicast::cluster arrives on the `empty` barrier of both).  The 580 -> 1024 layer is bound by
+// L2 -> SM traffic (12.5 GB per launch, 8.7 GB of it weight tiles re-read by each of the 244 M tiles).
+template <bool I64, int TNv, int kStagesV, int PW, int PF = 3, int CL = 1>
 __global__ void __launch_bounds__(PW * 32 + 64, PW == 8 ? (PF == 1 ? 3 : 2) : 1)
 gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long n_in_rows, const void* __restrict__ nbr,
                        int filter_size, long long n_out_rows, int c_in, int c_out, int kb_per_tap,
@@ -194,7 +199,7 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full_bar[s], (PW == 16 ? 1 : kProducerWarps) + 1);   // producer arrivals + the weight stream
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], CL);                                   // MMA completion of every CTA that receives the stage's weight tile
         }
         mbar_init(&accum_bar, 1);
         fence_mbar_init();
@@ -202,6 +207,7 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
     if (warp == kProducerWarps) tmem_alloc(&tmem_slot, tmem_cols);
     fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync();                                              // the peer's barriers exist before anything is multicast to them
     fence_after();
     const uint32_t tmem_d = tmem_slot;
     const uint32_t smem_base = smem_u32(smem);
@@ -313,7 +319,9 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
                 const uint32_t tmem_main = tmem_d + (uint32_t)(TN * (1 + g));
                 mbar_wait_a(full_a + 8 * stage, phase);
                 fence_after();
-                const uint32_t a_hi = (smem_base + stage * kStageBytes) >> 4;              // 16-byte units from here on
+                // (descriptor addresses are offsets inside the CTA's own shared window: in a cluster launch the 32-bit
+                // shared address of rank 1 carries the rank above bit 18)
+                const uint32_t a_hi = ((smem_base & 0x3ffffu) + stage * kStageBytes) >> 4;  // 16-byte units from here on
                 const uint32_t a_lo = a_hi + (kAHalf >> 4), b_hi = a_hi + (2 * kAHalf >> 4), b_lo = b_hi + (kBHalf >> 4);
                 if (elect_one()) {
 #pragma unroll
@@ -324,7 +332,8 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
                         umma_f16(tmem_d, dah, dbl, kIdescK, 1);
                         umma_f16(tmem_main, dah, dbh, kIdescK, j == 0 ? g == last_g : 1);
                     }
-                    umma_commit_a(empty_a + 8 * stage);
+                    if (CL > 1) umma_commit_mc(empty_a + 8 * stage, (uint16_t)((1u << CL) - 1));
+                    else umma_commit_a(empty_a + 8 * stage);
                 }
                 last_g = g;
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -341,7 +350,12 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
             for (int kb = 0; kb < n_kb; ++kb) {
                 mbar_wait_a(empty_a + 8 * stage, phase ^ 1);
                 mbar_arrive_expect_tx_a(full_a + 8 * stage, 2 * kBHalf);
-                bulk_load_a(smem_base + stage * kStageBytes + 2 * kAHalf, src, 2 * kBHalf, full_a + 8 * stage);
+                if (CL == 2) {                                          // this CTA's half (rank 0: W_hi, rank 1: W_lo) into both CTAs
+                    const uint32_t r = cluster_ctarank();
+                    bulk_load_mc(smem_base + stage * kStageBytes + 2 * kAHalf + r * kBHalf, src + r * kBHalf, kBHalf, full_a + 8 * stage, 3);
+                } else {
+                    bulk_load_a(smem_base + stage * kStageBytes + 2 * kAHalf, src, 2 * kBHalf, full_a + 8 * stage);
+                }
                 src += 2 * kBHalf;
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
@@ -446,6 +460,7 @@ gather_gemm_f16_kernel(const float* __restrict__ in, long long ld_in, long long 
     }
     fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync();                                              // no peer arrival / copy may land after this CTA is gone
     if (warp == kProducerWarps) {
         fence_after();
         tmem_dealloc(tmem_d, tmem_cols);
@@ -737,6 +752,8 @@ void set_attrs() {
     cudaFuncSetAttribute(gather_gemm_f16_kernel<false, 128, 3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (2 * kAHalf + 2 * 128 * TK * 2) + 1024);
     cudaFuncSetAttribute(gather_gemm_f16_kernel<true, 256, 4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (2 * kAHalf + 2 * 256 * TK * 2) + 1024);
     cudaFuncSetAttribute(gather_gemm_f16_kernel<false, 256, 4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (2 * kAHalf + 2 * 256 * TK * 2) + 1024);
+    cudaFuncSetAttribute(gather_gemm_f16_kernel<true, 256, 4, 16, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (2 * kAHalf + 2 * 256 * TK * 2) + 1024);
+    cudaFuncSetAttribute(gather_gemm_f16_kernel<false, 256, 4, 16, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (2 * kAHalf + 2 * 256 * TK * 2) + 1024);
     cudaFuncSetAttribute(wgrad_f16_kernel<true, 64, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, WCfg<64>::kSmemBytes);
     cudaFuncSetAttribute(wgrad_f16_kernel<false, 64, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, WCfg<64>::kSmemBytes);
     cudaFuncSetAttribute(wgrad_f16_kernel<true, 256, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WCfg<256>::kSmemBytes);
@@ -838,7 +855,30 @@ int hpl_blur_gemm_f16_amax(const float* in, int64_t ld_in, int64_t n_in_rows, co
         const float* k_bias = z > 1 ? nullptr : bias;
         const int k_act = z > 1 ? HPL_ACT_NONE : act;
         uint32_t* k_amax = z > 1 ? nullptr : out_amax;
-        if (idx64)
+        static int cluster_knob = -1;                           // HPL_WIDE_CLUSTER=1: pairs of M tiles share the weight stream (multicast)
+        if (cluster_knob < 0) { const char* e = getenv("HPL_WIDE_CLUSTER"); cluster_knob = e ? atoi(e) : 0; }
+        if (cluster_knob && m_tiles >= 2) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)((m_tiles + 1) / 2 * 2), (unsigned)n_tiles, (unsigned)z);   // (an odd last M tile gets an idle partner)
+            cfg.blockDim = dim3(kPW * 32 + 64);
+            cfg.dynamicSmemBytes = (size_t)smem;
+            cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            const int fs = (int)filter_size, ci = (int)c_in, co = (int)c_out, one = 1;
+            cudaError_t e;
+            if (idx64)
+                e = cudaLaunchKernelEx(&cfg, gather_gemm_f16_kernel<true, 256, kSt, kPW, 3, 2>, in, ld_in, n_in_rows, nbr, fs, n_out_rows, ci, co,
+                                       kb_per_tap, (const uint8_t*)image, k_bias, k_act, out, ld_out, out_channel_major, one, in_amax,
+                                       (const uint32_t*)w_amax, k_amax, kb_per_split);
+            else
+                e = cudaLaunchKernelEx(&cfg, gather_gemm_f16_kernel<false, 256, kSt, kPW, 3, 2>, in, ld_in, n_in_rows, nbr, fs, n_out_rows, ci, co,
+                                       kb_per_tap, (const uint8_t*)image, k_bias, k_act, out, ld_out, out_channel_major, one, in_amax,
+                                       (const uint32_t*)w_amax, k_amax, kb_per_split);
+            if (e != cudaSuccess) return (int)e;
+        } else if (idx64)
             gather_gemm_f16_kernel<true, 256, kSt, kPW><<<grid, kPW * 32 + 64, smem, s>>>(
                 in, ld_in, n_in_rows, nbr, (int)filter_size, n_out_rows, (int)c_in, (int)c_out, kb_per_tap, image, k_bias, k_act, out,
                 ld_out, out_channel_major, 1, in_amax, w_amax, k_amax, kb_per_split);

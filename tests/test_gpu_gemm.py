@@ -193,3 +193,16 @@ def test_wide_tile_wgrad_matches_float64(h, c, co, f):
     want = torch.einsum("fvc,vo->fco", g, dz[:, :co].double())
     assert_close(dw, want, "wide wgrad")
     assert_close(db, dz[:, :co].double().sum(0), "bias grad")
+
+
+def test_wide_tile_cluster_multicast_variant():
+    """HPL_WIDE_CLUSTER=1: the 256-wide tile launched as thread-block clusters of two M tiles that share the weight
+    stream (cp.async.bulk multicast + multicast tcgen05.commit).  The knob is read once per process -> subprocess; an odd
+    number of M tiles (idle partner CTA) and the split-K / ragged-Co case are included."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_gemm.py", "-q", "-m", "gpu", "-x", "-k", "test_wide_tile_engine2_matches_float64"]
+    out = subprocess.run(cmd, cwd=root, env=dict(os.environ, HPL_WIDE_CLUSTER="1"), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "4 passed" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

@@ -178,3 +178,43 @@ def test_engine5_operand_paths(knob):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "variant ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_engine5_at_bench_size_against_float64_rows_and_engine2():
+    """BASELINE configs[1] at the bench's size (32 concatenated 8192-point clouds, H ~ 242 k: 13 tiles per CTA, every
+    ring slot and accumulator buffer reused many times): forward, mirrored-tap data gradient and weight gradient of
+    engine 5 against a float64 evaluation on a sample of rows / the full reduction, and against engine 2."""
+    import bench
+    from hplflownet_b200.batching import concat_lattices
+    nbr = concat_lattices([bench.cloud_tables(s) for s in range(32)])["blur_neighbors"][0].to(DEV)
+    h = nbr.size(1)
+    plan = plans.build(nbr)
+    assert plan.usable and plan.symmetric and plan.n_tiles > 12 * 148
+    torch.manual_seed(3)
+    x = torch.randn(h, 64, device=DEV) * 3.0
+    w = torch.randn(15, 64, 64, device=DEV) * 0.04
+    b = torch.randn(64, device=DEV)
+    amax = ops.absmax(x)
+    x16 = ops.h16b_split(x, 64, amax)
+    y = ops.conv5(x16, plan, 64, w, b, ops.ACT_LEAKY, amax)
+    rows = torch.randint(0, h, (4096,), device=DEV)
+    xd = torch.cat((x.double(), torch.zeros(1, 64, dtype=torch.float64, device=DEV)), 0)
+    pre = torch.einsum("fvc,fco->vo", xd[nbr[:, rows].long()], w.double()) + b.double()
+    want = torch.where(pre > 0, pre, 0.1 * pre)
+    scale = y.abs().max().item()
+    assert (y[rows].double() - want).abs().max().item() <= 1e-5 * scale, "forward, sampled rows"
+    y2 = ops.blur_gemm(x, 64, nbr, h, w, b, ops.ACT_LEAKY, precision=2, x_amax=amax)
+    assert (y - y2).abs().max().item() <= 2e-5 * scale, "engine 5 vs engine 2"
+    dz = torch.randn(h, 64, device=DEV)
+    dz_amax = ops.absmax(dz)
+    dz16 = ops.h16b_split(dz, 64, dz_amax)
+    dx = ops.conv5(dz16, plan, 64, w.transpose(1, 2), None, ops.ACT_NONE, dz_amax, mirror=True)
+    tt = ops.transpose_table(nbr, h)
+    zd = torch.cat((dz.double(), torch.zeros(1, 64, dtype=torch.float64, device=DEV)), 0)
+    want_dx = torch.einsum("fvo,fco->vc", zd[tt[:, rows].long()], w.double())
+    assert (dx[rows].double() - want_dx).abs().max().item() <= 1e-5 * dx.abs().max().item(), "data gradient, sampled rows"
+    dw = ops.wgrad5(x16, dz16, plan, 64, 64, amax, dz_amax)
+    want_dw = torch.zeros(15, 64, 64, dtype=torch.float64, device=DEV)
+    for f in range(15):                                                          # (tap by tap: 242 k x 64 doubles at a time)
+        want_dw[f] = xd[nbr[f].long()].t() @ dz.double()
+    assert_close(dw, want_dw, "weight gradient, full reduction")

@@ -51,23 +51,32 @@ def _stream():
 
 
 class _Cloud:
-    """Device workspace of one cloud at one scale."""
+    """Device workspace of one cloud at one scale.  The tensors the caller receives (barycentric weights, el_minus_gr) are
+    separate allocations; everything that lives only during the build of this scale -- the hash table, the per-point
+    scratch, the vertex coordinates -- is carved out of ONE allocation and addressed by raw pointers (a scale used to make
+    ~14 allocator calls per cloud, ~0.3 ms of a 1.4 ms build)."""
 
     def __init__(self, pc, device):
         self.pc = pc                                    # (3, N) fp32 contiguous
         self.n = pc.size(1)
         n = self.n
+        L = _lib.load()
         self.bary = torch.empty((D1, n), dtype=torch.float32, device=device)
         self.emg = torch.empty((D1, n), dtype=torch.float32, device=device)
-        self.greedy = torch.empty((n, 4), dtype=torch.int32, device=device)
-        self.rankpack = torch.empty(n, dtype=torch.int32, device=device)
-        self.cap = _lib.load().hpl_lattice_table_capacity(n)
-        self.table_keys = torch.empty(self.cap, dtype=torch.int64, device=device)
-        self.table_first = torch.empty(self.cap, dtype=torch.int32, device=device)
-        self.table_ids = torch.empty(self.cap, dtype=torch.int32, device=device)
-        self.slot_of = torch.empty(4 * n, dtype=torch.int32, device=device)
-        self.scan_ws = torch.empty(_lib.load().hpl_lattice_scan_blocks(n), dtype=torch.int32, device=device)
-        self.vertex_coords = torch.empty((4 * n, 4), dtype=torch.int32, device=device)
+        self.cap = L.hpl_lattice_table_capacity(n)
+        sizes = (("greedy", n * 16), ("rankpack", n * 4), ("table_keys", self.cap * 8), ("table_first", self.cap * 4),
+                 ("table_ids", self.cap * 4), ("slot_of", 4 * n * 4), ("scan_ws", L.hpl_lattice_scan_blocks(n) * 4),
+                 ("vertex_coords", 4 * n * 16))
+        total = 0
+        offs = {}
+        for name, nbytes in sizes:
+            offs[name] = total
+            total += (nbytes + 255) // 256 * 256
+        self.scratch = torch.empty(total, dtype=torch.uint8, device=device)       # (cudaMalloc alignment: 256 B)
+        base = self.scratch.data_ptr()
+        self.greedy, self.rankpack = base + offs["greedy"], base + offs["rankpack"]
+        self.table_keys, self.table_first, self.table_ids = base + offs["table_keys"], base + offs["table_first"], base + offs["table_ids"]
+        self.slot_of, self.scan_ws, self.vertex_coords = base + offs["slot_of"], base + offs["scan_ws"], base + offs["vertex_coords"]
         self.offset = None
         self.h = None
 
@@ -103,23 +112,23 @@ class GenerateDataUnsymmetric(object):
     # ---- one scale -------------------------------------------------------------------------
     def _points(self, cloud, scale, key_minmax):
         _lib.call("hpl_lattice_points", cloud.pc.data_ptr(), cloud.n, float(scale), cloud.bary.data_ptr(),
-                  cloud.emg.data_ptr(), cloud.greedy.data_ptr(), cloud.rankpack.data_ptr(),
-                  key_minmax.data_ptr(), _stream())
+                  cloud.emg.data_ptr(), cloud.greedy, cloud.rankpack,
+                  key_minmax, _stream())
 
     def _insert(self, cloud, key_minmax, counts, slot):
         cloud.offset = torch.empty((D1, cloud.n), dtype=self.index_dtype, device=self.device)
-        _lib.call("hpl_lattice_insert", cloud.greedy.data_ptr(), cloud.rankpack.data_ptr(), cloud.n,
-                  key_minmax.data_ptr(), cloud.table_keys.data_ptr(), cloud.table_first.data_ptr(),
-                  cloud.table_ids.data_ptr(), cloud.cap, cloud.slot_of.data_ptr(), cloud.scan_ws.data_ptr(),
-                  cloud.offset.data_ptr(), int(self.index_dtype == torch.int64), cloud.vertex_coords.data_ptr(),
-                  counts[slot:].data_ptr(), _stream())
+        _lib.call("hpl_lattice_insert", cloud.greedy, cloud.rankpack, cloud.n,
+                  key_minmax, cloud.table_keys, cloud.table_first,
+                  cloud.table_ids, cloud.cap, cloud.slot_of, cloud.scan_ws,
+                  cloud.offset.data_ptr(), int(self.index_dtype == torch.int64), cloud.vertex_coords,
+                  counts + 4 * slot, _stream())
 
     def _neighbors(self, src, table, key_minmax, counts, slot, radius):
         offs = self._offsets_on_device(radius)
         f = offs.size(0)
         out = torch.empty((f, src.h), dtype=self.index_dtype, device=self.device)
-        _lib.call("hpl_lattice_neighbors", src.vertex_coords.data_ptr(), counts[slot:].data_ptr(), src.h,
-                  key_minmax.data_ptr(), table.table_keys.data_ptr(), table.table_ids.data_ptr(), table.cap,
+        _lib.call("hpl_lattice_neighbors", src.vertex_coords, counts + 4 * slot, src.h,
+                  key_minmax, table.table_keys, table.table_ids, table.cap,
                   offs.data_ptr(), f, out.data_ptr(), int(self.index_dtype == torch.int64), src.h, _stream())
         return out
 
@@ -127,15 +136,15 @@ class GenerateDataUnsymmetric(object):
         co, fo = self._offsets_on_device(corr_radius), self._offsets_on_device(filt_radius)
         p, f = co.size(0), fo.size(0)
         out = torch.empty((f, p, c1.h), dtype=self.index_dtype, device=self.device)
-        _lib.call("hpl_lattice_corr_table", c1.vertex_coords.data_ptr(), counts.data_ptr(), c1.h,
-                  key_minmax.data_ptr(), c2.table_keys.data_ptr(), c2.table_ids.data_ptr(), c2.cap,
+        _lib.call("hpl_lattice_corr_table", c1.vertex_coords, counts, c1.h,
+                  key_minmax, c2.table_keys, c2.table_ids, c2.cap,
                   co.data_ptr(), p, fo.data_ptr(), f, out.data_ptr(), int(self.index_dtype == torch.int64),
                   c1.h, _stream())
         return out
 
     def _next_points(self, cloud, scale):
         out = torch.empty((D, cloud.h), dtype=torch.float32, device=self.device)
-        _lib.call("hpl_lattice_next_points", cloud.vertex_coords.data_ptr(), cloud.h,
+        _lib.call("hpl_lattice_next_points", cloud.vertex_coords, cloud.h,
                   float(np.float32(self.expected_std * scale)), out.data_ptr(), _stream())
         return out
 
@@ -149,15 +158,16 @@ class GenerateDataUnsymmetric(object):
         n_scales = len(self.scales_filter_map)
         placeholder = lambda: torch.zeros(1, dtype=torch.long, device=dev)      # :450-459
         for idx, (scale, bcn_r, corr_f_r, corr_c_r) in enumerate(self.scales_filter_map):
-            key_minmax = torch.empty(8, dtype=torch.int32, device=dev)
-            counts = torch.empty(2, dtype=torch.int32, device=dev)
-            _lib.call("hpl_lattice_init_range", key_minmax.data_ptr(), _stream())
+            small = torch.empty(12, dtype=torch.int32, device=dev)               # key range (8 ints) | vertex counts (2 ints)
+            key_minmax = small.data_ptr()                                        # (raw pointers: no view tensors per call)
+            counts = key_minmax + 32
+            _lib.call("hpl_lattice_init_range", key_minmax, _stream())
             c1, c2 = _Cloud(last1, dev), _Cloud(last2, dev)
             self._points(c1, scale, key_minmax)
             self._points(c2, scale, key_minmax)
             self._insert(c1, key_minmax, counts, 0)
             self._insert(c2, key_minmax, counts, 1)
-            c1.h, c2.h = [int(x) for x in counts.tolist()]                       # the one sync per scale
+            c1.h, c2.h = [int(x) for x in small[8:10].tolist()]                  # the one sync per scale
 
             if bcn_r != -1:
                 blur1 = self._neighbors(c1, c1, key_minmax, counts, 0, bcn_r)

@@ -74,7 +74,7 @@ def _backward_single_layer5(dx, xs, chans, layer, first_nbr_t, need_input_grad, 
     arena = dz_bound[2] if len(dz_bound) > 2 else None                 # pre-zeroed small outputs (one fill for all of them)
     db = None
     if need_param_grad and b is not None:
-        db = arena["db"] if arena is not None else dx.new_zeros(chans[1])
+        db = arena["db"] if arena is not None else ops.small_zeros(chans[1], dx.dtype, dx.device)
     dz_amax = arena["dz_amax"] if arena is not None else ops.amax_slots(dx.device, 1)
     dz16 = ops.h16b_split_ex(dx, chans[1], dz_bound[0], y=xs[1] if act != ops.ACT_NONE else None, act=act,
                              amax_b=dz_bound[1], amax_out=dz_amax, colsum=db, dispose=1 if keep_fp32 else 2)
@@ -117,7 +117,7 @@ def backward(dx, xs, chans, layers, n_rows, first_nbr, first_nbr_t, need_input_g
             # one pass: activation backward, max|dz| (operand scale of wgrad and dgrad) and the bias gradient
             dz_amax = ops.amax_slots(dx.device, 1) if (split or on5) else None
             if need_param_grad[l] and b is not None:
-                db_fused = dx.new_zeros(chans[l + 1])
+                db_fused = ops.small_zeros(chans[l + 1], dx.dtype, dx.device)
             if act != ops.ACT_NONE or dz_amax is not None or db_fused is not None:
                 ops.act_backward_stats_(dx, xs[l + 1] if act != ops.ACT_NONE else None, chans[l + 1], act, dz_amax, db_fused)
         else:
@@ -135,7 +135,7 @@ def backward(dx, xs, chans, layers, n_rows, first_nbr, first_nbr_t, need_input_g
                 dw = ops.wgrad5(x16, dz16, plan, chans[0], chans[1], x_amax, dz_amax)
                 db = db_fused
                 if b is not None and db is None:
-                    db = dx.new_zeros(chans[1])
+                    db = ops.small_zeros(chans[1], dx.dtype, dx.device)
                     ops.column_sums_(dx, chans[1], db)
                 grads[0] = (dw, db)
             if need_input_grad:

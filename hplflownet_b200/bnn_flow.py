@@ -160,7 +160,7 @@ class _CorrFunction(torch.autograd.Function):
             dw0 = torch.cat((dwa, dwb), 0).permute(2, 0, 1)                                   # (O, C1 + C, P)
             grads[0] = dw0.reshape(ctx.param_shapes[0]).contiguous()
             # conv3d bias: every (f, v) output position sees it once
-            db0 = torch.zeros(wp, dtype=torch.float32, device=dev)
+            db0 = ops.small_zeros(wp, torch.float32, dev)
             _lib.call("hpl_column_sums", dz.data_ptr(), dz.stride(0), dz.size(0), wp, db0.data_ptr(), ops._stream())
             grads[1] = db0[:o1].contiguous()
 

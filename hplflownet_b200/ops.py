@@ -137,6 +137,8 @@ class _timed:
 
 def _stream_of(device):
     """raw handle of the current stream of `device`"""
+    if not isinstance(device, torch.device):
+        device = torch.device(device)
     idx = device.index
     return torch._C._cuda_getCurrentRawStream(idx if idx is not None else torch._C._cuda_getDevice())
 
@@ -205,7 +207,7 @@ def scatter_rows(x, bary, off, n_rows, want_wsum, in_amax=None, rows=None, wsum=
     if rows is None:
         rows = alloc_rows(n_rows, c, x.device, zero=True)
     if want_wsum and wsum is None:
-        wsum = torch.zeros(n_rows, dtype=torch.float32, device=x.device)
+        wsum = small_zeros(n_rows, torch.float32, x.device)
     with _timed("scatter"):
         _lib.call("hpl_scatter_rows", x.data_ptr(), bary.data_ptr(), off.data_ptr(), i64, n, c,
                   rows.data_ptr(), rows.stride(0), n_rows, wsum.data_ptr() if want_wsum else None,
@@ -221,13 +223,40 @@ def zero_arena(device, spec):
     for _, n, _ in spec:
         offs.append(total)
         total += (int(n) + 3) // 4 * 4
-    buf = torch.zeros(max(total, 4), dtype=torch.float32, device=device)
+    buf = small_zeros(max(total, 4), torch.float32, device)
     return {name: buf[o:o + int(n)].view(dt) for (name, n, dt), o in zip(spec, offs)}
+
+
+# Small zeroed buffers (statistic slots, bias gradients, weight sums): a training step of the full model asked torch for
+# ~2000 of them -- one fill kernel and ~10 us of launch path each.  They are carved from a zeroed chunk instead (a bump
+# pointer per device and stream; a chunk is never reused, its views keep it alive).  Not during CUDA-graph capture: there
+# every buffer must be zeroed by a node of the graph that uses it.
+_ZERO_CHUNK_WORDS = 1 << 18                     # 1 MB
+_SMALL_ZERO_MAX = 1 << 14                       # words; larger requests go to torch.zeros
+_zero_chunks = {}
+
+
+def small_zeros(n, dtype, device):
+    """n zeroed elements of a 4-byte dtype (16-byte aligned)."""
+    n = int(n)
+    if n > _SMALL_ZERO_MAX or torch.cuda.is_current_stream_capturing():
+        return torch.zeros(n, dtype=dtype, device=device)
+    if not isinstance(device, torch.device):
+        device = torch.device(device)
+    key = (device.index, _stream_of(device))
+    st = _zero_chunks.get(key)
+    need = (max(n, 1) + 3) // 4 * 4
+    if st is None or st[1] + need > _ZERO_CHUNK_WORDS:
+        st = [torch.zeros(_ZERO_CHUNK_WORDS, dtype=torch.int32, device=device), 0]
+        _zero_chunks[key] = st
+    v = st[0][st[1]:st[1] + n]
+    st[1] += need
+    return v if dtype == torch.int32 else v.view(dtype)
 
 
 def amax_slots(device, n):
     """n zeroed device scalars for the fused max|x| statistics (kernels RED.MAX into them); index with [i:i+1]."""
-    return torch.zeros(n, dtype=torch.int32, device=device)
+    return small_zeros(n, torch.int32, device)
 
 
 def fused_stats():
@@ -376,7 +405,7 @@ def blur_wgrad(x, c_in, nbr, n_out_rows, dz, c_out, filter_size, want_db=True, p
     else:
         nbr_ptr, i64 = None, 0
     dw = torch.zeros((filter_size, c_in, c_out), dtype=torch.float32, device=x.device)
-    db = torch.zeros(c_out, dtype=torch.float32, device=x.device) if want_db else None
+    db = small_zeros(c_out, torch.float32, x.device) if want_db else None
     if precision is None:
         precision = DEFAULT_PRECISION
     if precision in (4, 5):                  # engines 4 / 5 cover other roles; dW of these layers is register-staged
@@ -455,7 +484,7 @@ def channel_sums(x, out=None):
     """Row sums of x (C, N); out: a zeroed (C,) tensor to accumulate into."""
     _f32(x, "x")
     c, n = x.shape
-    s = out if out is not None else torch.zeros(c, dtype=torch.float32, device=x.device)
+    s = out if out is not None else small_zeros(c, torch.float32, x.device)
     _lib.call("hpl_channel_sums", x.data_ptr(), c, n, s.data_ptr(), _stream())
     return s
 

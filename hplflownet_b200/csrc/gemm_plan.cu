@@ -970,12 +970,15 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad5_kernel(const Wgrad5Args p)
             cp_async_arrive_noinc(bfull);
             load_dz_half(0, 1, b_base + kWBHalf);
             cp_async_arrive_noinc(bfull + 8);
+            if (n_my > 1) fetch_rows(1);
         }
         int stage = 0;
         uint32_t phase_bit = 0;
         for (int k = 0; k < n_my; ++k) {
+            // (urow holds the row list of tile k + 1: it was fetched at stage 4 of tile k - 1.  Read at the top of the tile
+            // that uses it, the cold list -- two dependent DRAM round trips, the count and then the rows -- stalled every copy
+            // warp at stage 0 of every tile.)
             const bool has_next = k + 1 < n_my;
-            if (has_next) fetch_rows(k + 1);
             wait_bar(ufull + 8 * (k & 1), (k >> 1) & 1);
             const uint32_t ub = u_base + (k & 1) * kUBuf + src_off;
             const uint32_t ubn = u_base + ((k + 1) & 1) * kUBuf;
@@ -1004,6 +1007,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad5_kernel(const Wgrad5Args p)
                             load_rows(ubn, 4 * s);
                             if (s == 3) cp_async_arrive_noinc(ufull + 8 * ((k + 1) & 1));
                         }
+                        if (s == 4 && k + 2 < n_my) fetch_rows(k + 2);           // (urow is free again: its last use was stage 3)
                         if (s == 5) {                                             // stage 3 (last user of dz half 0) has completed
                             wait_bar(ufull + 8 * ((k + 1) & 1), ((k + 1) >> 1) & 1);  // next tile's row block (issued at stage 0)
                             load_dz_half(k + 1, 0, b_base);

@@ -858,7 +858,7 @@ struct Wgrad5Args {
     const uint32_t* x_amax;
     const uint32_t* dz_amax;
     int n_tiles, cb_count, cbo_count, filter_size, c_in, c_out, tiles_per_cta;
-    int dbg;                      // timing experiments (HPL_WGRAD5_DBG): 1 no fence.proxy.async, 4 no MMAs, 8 no operand stores
+    int dbg;                      // timing experiments (HPL_WGRAD5_DBG): 1 no fence.proxy.async, 4 no MMAs, 8 no operand stores, 16 no row reads, 32 no slot reads
 };
 
 __global__ void __launch_bounds__(kThreads, 1) wgrad5_kernel(const Wgrad5Args p) {
@@ -992,9 +992,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad5_kernel(const Wgrad5Args p)
                     uint32_t slot[8];
                     uint4 v[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) slot[i] = lds_u16(ibs + ((4 * mt + (i >> 1)) * TM + h * 64 + (i & 1) * 32) * 2);
+                    for (int i = 0; i < 8; ++i) slot[i] = (p.dbg & 32) ? (uint32_t)i : lds_u16(ibs + ((4 * mt + (i >> 1)) * TM + h * 64 + (i & 1) * 32) * 2);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = lds128(ub + slot[i] * kURow);
+                    for (int i = 0; i < 8; ++i) v[i] = (p.dbg & 16) ? make_uint4(slot[i], 0, 0, 0) : lds128(ub + slot[i] * kURow);
                     // MMAs of stage s - 2 are complete once the stage buffer is free.  s == 1: the previous tile's last stage
                     // (h = 1, mt = 3) is done -> the dz half-1 buffer may be refilled; s == 5: half 0 of this tile is done.
                     wait_bar(empty + 8 * stage, phase_bit ^ 1);                  // (every lane polls: a lane-0 wait leaves the warp diverged)

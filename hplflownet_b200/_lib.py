@@ -77,7 +77,8 @@ LAUNCHES = {
     "hpl_scatter_rows": 1, "hpl_normalize_rows": 2, "hpl_gather_rows": 1, "hpl_blur_gemm": 1, 
     "hpl_blur_wgrad": 2, "hpl_absmax": 1, "hpl_blur_gemm_f16_amax": 3, "hpl_normalize_rows_amax": 2, "hpl_cm_to_rows_amax": 1, "hpl_act_backward_stats": 1,
     "hpl_h16_split": 1, "hpl_blur_gemm_tma": 3, "hpl_blur_gemm_f16": 3, "hpl_blur_wgrad_f16": 2, "hpl_act_backward": 1, "hpl_transpose_table": 1, "hpl_cm_to_rows": 1,
-    "hpl_rows_to_cm": 1, "hpl_channel_sums": 1, "hpl_fill_zero": 1, "hpl_fill_i32": 1,
+    "hpl_rows_to_cm": 1, "hpl_channel_sums": 1, "hpl_fill_zero": 0, "hpl_fill_i32": 1,       # (hpl_fill_zero is a cudaMemsetAsync, not a kernel of this library)
+   
     "hpl_corr_gather": 1, "hpl_corr_scatter": 1, "hpl_column_sums": 1,
     "hpl_lattice_init_range": 1, "hpl_lattice_points": 1, "hpl_lattice_insert": 6,
     "hpl_lattice_neighbors": 1, "hpl_lattice_corr_table": 1, "hpl_lattice_next_points": 1,

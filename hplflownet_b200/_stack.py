@@ -77,7 +77,9 @@ def _backward_single_layer5(dx, xs, chans, layer, first_nbr_t, need_input_grad, 
         db = arena["db"] if arena is not None else ops.small_zeros(chans[1], dx.dtype, dx.device)
     dz_amax = arena["dz_amax"] if arena is not None else ops.amax_slots(dx.device, 1)
     dz16 = ops.h16b_split_ex(dx, chans[1], dz_bound[0], y=xs[1] if act != ops.ACT_NONE else None, act=act,
-                             amax_b=dz_bound[1], amax_out=dz_amax, colsum=db, dispose=1 if keep_fp32 else 2)
+                             amax_b=dz_bound[1], amax_out=dz_amax, colsum=db, dispose=1 if keep_fp32 else ops.dispose_mode(dx))
+    if not keep_fp32:
+        ops.recycle_rows(dx)        # (a large accumulator is zeroed on the side stream, under the two gradient kernels)
     grads = [None]
     if need_param_grad:
         grads[0] = (ops.wgrad5(x16, dz16, plan, chans[0], chans[1], x_amax, dz_amax, out=arena["dw"] if arena is not None else None), db)
@@ -91,8 +93,6 @@ def _backward_single_layer5(dx, xs, chans, layer, first_nbr_t, need_input_grad, 
             out = ops.conv5(dz16, plan, chans[1], wd, None, ops.ACT_NONE, dz_amax, mirror=True, tag="dgrad")
         else:
             out = ops.blur_gemm(dx, chans[1], first_nbr_t(), plan.n_in_rows, wd, None, ops.ACT_NONE, tag="dgrad", x_amax=dz_amax)
-    if not keep_fp32:
-        ops.release_zero_rows(dx)
     return out, grads
 
 

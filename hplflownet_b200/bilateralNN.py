@@ -114,8 +114,9 @@ class _BCLFunction(torch.autograd.Function):
                 lat_amax, wsum_amax = z["x_amax"], z["w_amax"]
                 raw, wsum = ops.scatter_rows(feat, bary_i, off_i, h, True, in_amax=lat_amax, rows=raw, wsum=z["wsum"])
                 inv = torch.empty_like(wsum)
-                x16 = ops.h16b_split_ex(raw, c_in, lat_amax, norm=wsum, inv_out=inv, norm_amax_out=wsum_amax, dispose=2)
-                ops.release_zero_rows(raw)
+                x16 = ops.h16b_split_ex(raw, c_in, lat_amax, norm=wsum, inv_out=inv, norm_amax_out=wsum_amax,
+                                        dispose=ops.dispose_mode(raw))
+                ops.recycle_rows(raw)
                 first5 = _stack.First5(x16, lat_amax, plan)
             else:
                 lat, wsum = ops.scatter_rows(feat, bary_i, off_i, h, use_norm)
@@ -152,6 +153,7 @@ class _BCLFunction(torch.autograd.Function):
         ctx.idx = (bary_i, off_i, nbr2, bary_o, off_o)
         ctx.has_slice_bias = slice_bias is not None
         ctx.param_shapes = [p.shape for p in params]
+        ops.join_side(feat.device)                               # (a large accumulator was zeroed on the side stream meanwhile)
         return out.unsqueeze(0)
 
     @staticmethod
@@ -197,6 +199,7 @@ class _BCLFunction(torch.autograd.Function):
                 d_feat = ops.gather_rows(dx, chans[0], bary_i, off_i, ctx.inv, None).unsqueeze(0)
             else:
                 d_feat = ops.rows_to_cm(dx, chans[0]).unsqueeze(0)
+        ops.join_side(g.device)
         return (None, d_feat, None, None, None, None, None, d_slice_bias, *grads)
 
 

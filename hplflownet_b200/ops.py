@@ -185,6 +185,7 @@ def zero_rows(n_rows, channels, device):
     key = (device.index, _stream_of(device), n_rows, ld)
     free = _zero_pool.get(key)
     if free:
+        join_side(device)
         return free.pop()
     return torch.zeros((n_rows, ld), dtype=torch.float32, device=device)
 
@@ -195,6 +196,58 @@ def release_zero_rows(t):
     free = _zero_pool.setdefault(key, [])
     if len(free) < 4:
         free.append(t)
+
+
+# Large accumulators are not re-zeroed by their consumer (the zero stores were 40 % of the fused split pass's traffic, which
+# runs at DRAM speed) but by a fill on a SIDE stream, concurrently with the contraction kernel that follows on the main
+# stream (issue / latency bound, it leaves the DRAM bandwidth unused).  The side stream is forked from and joined back into
+# the current stream (join_side: end of the module's forward / backward, and before any buffer leaves the pool), so the
+# pattern is also legal inside a CUDA-graph capture, where it becomes a parallel branch.
+SIDE_ZERO_MIN_BYTES = 16 << 20
+_side_streams = {}
+_side_dirty = {}
+
+
+def dispose_mode(t):
+    """dispose argument of hpl_h16b_split_ex for an accumulator that goes back to the zero pool: 2 = the kernel zeroes it,
+    0 = recycle_rows will (large buffers)."""
+    return 0 if t.numel() * 4 >= SIDE_ZERO_MIN_BYTES else 2
+
+
+_stream_objs = {}
+
+
+def _cur_stream_obj(device):
+    """torch Stream object of the current stream (cached per raw handle: building one costs ~10 us)."""
+    raw = _stream_of(device)
+    key = (device.index, raw)
+    obj = _stream_objs.get(key)
+    if obj is None:
+        obj = _stream_objs[key] = torch.cuda.current_stream(device)
+    return obj, key
+
+
+def recycle_rows(t):
+    """Give back an accumulator whose consumer has been enqueued on the current stream: zeroed here on the side stream
+    (large buffers, see above) or already zeroed by the consumer (dispose_mode(t) == 2)."""
+    if t.numel() * 4 >= SIDE_ZERO_MIN_BYTES:
+        cur, key = _cur_stream_obj(t.device)
+        side = _side_streams.get(key)
+        if side is None:
+            side = _side_streams[key] = torch.cuda.Stream(t.device)
+        side.wait_stream(cur)
+        _lib.call("hpl_fill_zero", t.data_ptr(), t.numel() * 4, side.cuda_stream)
+        _side_dirty[key] = side
+    release_zero_rows(t)
+
+
+def join_side(device):
+    """Order the side stream's fills before whatever follows on the current stream."""
+    if _side_dirty:
+        cur, key = _cur_stream_obj(device)
+        side = _side_dirty.pop(key, None)
+        if side is not None:
+            cur.wait_stream(side)
 
 
 def scatter_rows(x, bary, off, n_rows, want_wsum, in_amax=None, rows=None, wsum=None):

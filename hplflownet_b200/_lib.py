@@ -62,6 +62,7 @@ SIGNATURES = {
     "hpl_conv5_workspace": [i64],
     "hpl_conv5_supported": [i64, i64, i64],
     "hpl_conv5": [vp, vp, i64, i64, i64, i64, vp, i64, i64, i64, vp, vp, cint, vp, i64, vp, cint, vp, vp, vp],
+    "hpl_conv5_weights": [vp, i64, i64, i64, i64, i64, i64, vp, vp, vp],
     "hpl_wgrad5": [vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp],
     "hpl_fill_zero": [vp, i64, vp],
     "hpl_fill_i32": [vp, i64, i32, vp],

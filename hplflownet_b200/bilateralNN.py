@@ -109,6 +109,8 @@ class _BCLFunction(torch.autograd.Function):
                 # combination, bilateralNN.py:150-186), so the splat kernel's fused max|feat| is a valid operand scale.
                 # One pass turns the accumulators into the normalised image, writes 1 / (wsum + 1e-5) for the backward, records
                 # max wsum and zeroes the accumulator again (it returns to the zero pool: no memset per call).
+                if h * c_in * 4 >= ops.SIDE_ZERO_MIN_BYTES:
+                    ops.conv5_prepare(layers[0][0])              # weight image on a side stream, under the splat
                 raw = ops.zero_rows(h, c_in, feat.device)
                 z = ops.zero_arena(feat.device, [("wsum", h, torch.float32), ("x_amax", 1, torch.int32), ("w_amax", 1, torch.int32)])
                 lat_amax, wsum_amax = z["x_amax"], z["w_amax"]
@@ -169,6 +171,9 @@ class _BCLFunction(torch.autograd.Function):
                 # |dz[v]| <= max|g| x (sum of barycentric weights at v): the splat's fused max|g| and the forward's max wsum
                 # give the operand scale of dz without a pass over it; the accumulator comes from the zero pool
                 w0 = layers[0][0]
+                if (ctx.needs_input_grad[1] and h * chans[-1] * 4 >= ops.SIDE_ZERO_MIN_BYTES and ctx.first5.plan.symmetric
+                        and ops.conv5_supported(w0.size(0), chans[1], chans[0])):
+                    ops.conv5_prepare(w0.transpose(1, 2), mirror=True)   # the data gradient's weight image, under the splat of g
                 arena = ops.zero_arena(g.device, [("g_amax", 1, torch.int32), ("dz_amax", 1, torch.int32),
                                                   ("dw", w0.numel(), torch.float32), ("db", chans[-1], torch.float32),
                                                   ("dsb", chans[-1], torch.float32)])

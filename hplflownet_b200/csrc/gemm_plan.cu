@@ -1188,6 +1188,23 @@ int hpl_conv5_supported(int64_t filter_size, int64_t c_in, int64_t c_out) {
 /* out[row, :] = act(bias + sum_f x[nbr[f, row]] . w[f]) for every row of the plan's table; x16 = h16b image of x.
  * w: element (f, c, o) at w + f * w_sf + c * w_sc + o * w_so.  tap_map (device, F ints) or NULL.
  * workspace: hpl_conv5_workspace(c_in) bytes, 128-byte aligned; workspace_valid != 0: its weight image is current. */
+/* Weight image of hpl_conv5 built ahead of the call (e.g. on a side stream while the splat runs): max|w| + the tile image
+ * into `workspace`; hpl_conv5 is then called with workspace_valid = 1. */
+int hpl_conv5_weights(const float* w, int64_t w_sf, int64_t w_sc, int64_t w_so, int64_t filter_size, int64_t c_in, int64_t c_out,
+                      const int32_t* tap_map, void* workspace, void* stream) {
+    HPL_CHECK_ARG(w && workspace && ((uintptr_t)workspace & 127) == 0);
+    HPL_CHECK_ARG(hpl_conv5_supported(filter_size, c_in, c_out));
+    const int cb = cb_of(c_in);
+    uint8_t* image = reinterpret_cast<uint8_t*>(workspace);
+    uint32_t* w_amax = reinterpret_cast<uint32_t*>(image + (long long)cb * kTaps * kBTap);
+    const int rc = hpl_absmax(w, filter_size * c_in * c_out, w_amax, stream);
+    if (rc != 0) return rc;
+    const long long total = (long long)cb * kTaps * 64 * 4;
+    weight_image5_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(w, w_sf, w_sc, w_so, (int)filter_size, (int)c_in,
+                                                                                         (int)c_out, cb, tap_map, w_amax, image);
+    HPL_RETURN_LAST();
+}
+
 int hpl_conv5(const void* x16, const void* plan, int64_t n_out_rows, int64_t filter_size, int64_t c_in, int64_t c_out,
               const float* w, int64_t w_sf, int64_t w_sc, int64_t w_so, const int32_t* tap_map, const float* bias, int act,
               float* out, int64_t ld_out, void* workspace, int workspace_valid, const uint32_t* in_amax, uint32_t* out_amax,
@@ -1204,11 +1221,8 @@ int hpl_conv5(const void* x16, const void* plan, int64_t n_out_rows, int64_t fil
     uint32_t* w_amax = reinterpret_cast<uint32_t*>(image + (long long)cb * kTaps * kBTap);
     if (!workspace_valid) {
         // max|w| over the (possibly strided) weight: the buffer behind a dense permutation holds exactly the F*C*Co values
-        const int rc = hpl_absmax(w, filter_size * c_in * c_out, w_amax, stream);
+        const int rc = hpl_conv5_weights(w, w_sf, w_sc, w_so, filter_size, c_in, c_out, tap_map, workspace, stream);
         if (rc != 0) return rc;
-        const long long total = (long long)cb * kTaps * 64 * 4;
-        weight_image5_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w, w_sf, w_sc, w_so, (int)filter_size, (int)c_in, (int)c_out,
-                                                                           cb, tap_map, w_amax, image);
     }
     const uint8_t* pb = reinterpret_cast<const uint8_t*>(plan);
     Conv5Args a;

@@ -564,6 +564,44 @@ def _mirror_map(filter_size, device):
     return t if t is not None else False
 
 
+# Weight images built ahead of their contraction on a second side stream (ops.conv5_prepare): in a training step the
+# weights change every step, so max|w| + the tile image are two small latency-bound kernels in front of every hpl_conv5;
+# forked at the start of the module's forward / backward they run under the splat instead.
+_weight_side = {}
+_prepared = {}
+
+
+def _wkey(w, mirror):
+    return (w.data_ptr(), tuple(w.shape), tuple(w.stride()), bool(mirror))
+
+
+def conv5_prepare(w, mirror=False):
+    """Enqueue the weight image of a coming ops.conv5(w, mirror=...) call on the weight side stream (forked from the
+    current stream here); that call joins the stream and uses the image."""
+    f, c, co = w.shape
+    # (only while a CUDA graph is being captured: there the fork / join are graph edges and cost nothing at replay; launched
+    # eagerly, their host-side cost -- three stream operations -- exceeds the two small kernels they hide)
+    if not torch.cuda.is_current_stream_capturing() or not _dense_permutation(w):
+        return
+    nbytes = _lib.load().hpl_conv5_workspace(c) + 256
+    ws, ws_valid, commit = _cached_workspace(w, nbytes, ("e5", mirror))
+    if ws_valid:
+        return
+    if commit is _no_commit:                                          # (the shared per-stream scratch may be rewritten before the call)
+        ws = torch.empty(nbytes // 4 + 4, dtype=torch.float32, device=w.device)
+    tap_map = _mirror_map(f, w.device) if mirror else None
+    if tap_map is False:
+        return
+    cur, key = _cur_stream_obj(w.device)
+    side = _weight_side.get(key)
+    if side is None:
+        side = _weight_side[key] = torch.cuda.Stream(w.device)
+    side.wait_stream(cur)
+    _lib.call("hpl_conv5_weights", w.data_ptr(), w.stride(0), w.stride(1), w.stride(2), f, c, co,
+              tap_map.data_ptr() if tap_map is not None else None, ws.data_ptr(), side.cuda_stream)
+    _prepared[_wkey(w, mirror)] = (ws, commit, side, cur)
+
+
 def conv5(x16, plan, c_in, w, bias, act, x_amax, out=None, out_amax=None, mirror=False, tag="fwd"):
     """Engine 5 (csrc/gemm_plan.cu): out[v] = act(bias + sum_f x[nbr[f, v]] @ w[f_or_mirror(f)]) over plan's table.
     x16: h16b image of x; w (F, C, Co) any dense permutation; mirror=True uses w[mirror(f)] (data gradient)."""
@@ -577,7 +615,13 @@ def conv5(x16, plan, c_in, w, bias, act, x_amax, out=None, out_amax=None, mirror
         assert tap_map is not False
     if not _dense_permutation(w):
         w = w.contiguous()
-    ws, ws_valid, commit = _cached_workspace(w, _lib.load().hpl_conv5_workspace(c) + 256, ("e5", mirror))
+    prep = _prepared.pop(_wkey(w, mirror), None) if _prepared else None
+    if prep is not None:                                              # image built on the weight side stream: join it
+        ws, commit, side, cur = prep
+        cur.wait_stream(side)
+        ws_valid = 1
+    else:
+        ws, ws_valid, commit = _cached_workspace(w, _lib.load().hpl_conv5_workspace(c) + 256, ("e5", mirror))
     with _timed(tag):
         _lib.call("hpl_conv5", x16.data_ptr(), plan.buf.data_ptr(), plan.n_rows, f, c, co,
                   w.data_ptr(), w.stride(0), w.stride(1), w.stride(2),

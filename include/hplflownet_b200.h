@@ -203,6 +203,11 @@ int hpl_h16b_split_ex(float* x, int64_t ld, int64_t n_rows, int64_t channels, co
                       const uint32_t* amax_b, uint32_t* amax_out, float* colsum, int dispose, void* x16,
                       void* stream);
 
+/* The weight part of hpl_conv5 alone: max|w| and the tile image of w into `workspace` (hpl_conv5_workspace bytes).  Lets a
+ * caller build it ahead of time -- on another stream, while the splat runs -- and call hpl_conv5 with workspace_valid = 1. */
+int hpl_conv5_weights(const float* w, int64_t w_sf, int64_t w_sc, int64_t w_so, int64_t filter_size, int64_t c_in,
+                      int64_t c_out, const int32_t* tap_map, void* workspace, void* stream);
+
 /* out[row,:] = act(bias + sum_f x[nbr[f,row]] . w[f]) over the plan's table; x16 = h16b image of x (n_in_rows, c_in).
  * w element (f,c,o) at w + f*w_sf + c*w_sc + o*w_so; tap_map (device, F int32, may be NULL): kernel tap g uses
  * w[tap_map[g]] (data gradient: mirrored tap, transposed weight).  workspace: hpl_conv5_workspace(c_in) bytes,

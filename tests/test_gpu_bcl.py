@@ -278,3 +278,42 @@ def test_engine5_module_matches_engine2_and_plans_on_second_use(monkeypatch):
     assert_close(third[0], first[0], "engine 2 again, output")
     for a, b in zip(third[1:], first[1:]):
         assert_close_grad(a, b, "engine 2 again, gradient")
+
+
+def test_graph_replay_of_the_step_matches_eager_launches():
+    """The bench's headline number is ONE CUDA-graph replay of forward + backward (bench.py, graphs.GraphedStep).  At a
+    size where the large-buffer paths are active (accumulators re-zeroed on a forked side stream, weight images built on a
+    second side stream during capture, zero pool reused across replays): replays with fresh inputs must reproduce the
+    eagerly launched step -- outputs, input gradient and every parameter gradient."""
+    import bench
+    from hplflownet_b200 import ops, plans
+    from hplflownet_b200.graphs import GraphedStep
+    mod = bench.make_state().to(DEV)
+    _, res, gy, n_tot, h_tot = bench.make_batch(torch.device(DEV), list(range(12)))
+    assert h_tot * 64 * 4 >= ops.SIDE_ZERO_MIN_BYTES
+    plans.prepare(res["blur_neighbors"])
+    params = list(mod.parameters())
+
+    def step():
+        for p in params:
+            p.grad = None
+        res["features"].grad = None
+        y = mod(res["features"], res["barycentric"], res["lattice_offset"], res["blur_neighbors"], res["barycentric"], res["lattice_offset"])
+        y.backward(gy)
+        return [y.detach(), res["features"].grad] + [p.grad for p in params]      # (a replay refills exactly these buffers)
+
+    graphed = GraphedStep(step)
+    torch.manual_seed(77)
+    for trial in range(3):
+        with torch.no_grad():
+            res["features"].copy_(torch.randn_like(res["features"]) * (1.0 + trial))
+            gy.copy_(torch.randn_like(gy))
+            if trial == 2:
+                for p in params:                         # the weights change between replays too (a training loop)
+                    p.add_(torch.randn_like(p) * 0.01)
+        got = [t.clone() for t in graphed.replay()]
+        want = [t.clone() for t in step()]
+        for i, (a, b) in enumerate(zip(got, want)):
+            scale = b.abs().max().item()
+            # (fp32 RED accumulation order differs from run to run: not bitwise)
+            assert (a - b).abs().max().item() <= 2e-5 * scale + 1e-12, "tensor %d of trial %d: %g vs scale %g" % (i, trial, (a - b).abs().max().item(), scale)

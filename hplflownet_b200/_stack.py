@@ -80,6 +80,8 @@ def _backward_single_layer5(dx, xs, chans, layer, first_nbr_t, need_input_grad, 
                              amax_b=dz_bound[1], amax_out=dz_amax, colsum=db, dispose=1 if keep_fp32 else ops.dispose_mode(dx))
     if not keep_fp32:
         ops.recycle_rows(dx)        # (a large accumulator is zeroed on the side stream, under the two gradient kernels)
+    if arena is not None and "_after_split" in arena:
+        arena.pop("_after_split")()                               # (side-stream work the caller deferred to this point)
     grads = [None]
     if need_param_grad:
         grads[0] = (ops.wgrad5(x16, dz16, plan, chans[0], chans[1], x_amax, dz_amax, out=arena["dw"] if arena is not None else None), db)

@@ -180,10 +180,19 @@ class _BCLFunction(torch.autograd.Function):
                 dx = ops.zero_rows(h, chans[-1], g.device)
                 dx, _ = ops.scatter_rows(g, bary_o, off_o, h, False, in_amax=arena["g_amax"], rows=dx)
                 dz_bound = (arena["g_amax"], ctx.wsum_amax, arena)
+                if ctx.has_slice_bias and ctx.needs_input_grad[7]:
+                    d_slice_bias = arena["dsb"]
+                    if g.numel() * 4 >= ops.SIDE_ZERO_MIN_BYTES and torch.cuda.is_current_stream_capturing():
+                        # the slice bias gradient (a reduction over g, DRAM bound) runs on the side stream after the split
+                        # pass, under the weight-gradient kernel (latency bound) -- see _stack._backward_single_layer5.  (Only
+                        # while a graph is captured: launched eagerly, the fork costs more host time than it hides.)
+                        arena["_after_split"] = lambda: ops.channel_sums(g, out=d_slice_bias, side=True)
+                    else:
+                        ops.channel_sums(g, out=d_slice_bias)
             else:
                 dx, _ = ops.scatter_rows(g, bary_o, off_o, h, False)
-            if ctx.has_slice_bias and ctx.needs_input_grad[7]:
-                d_slice_bias = ops.channel_sums(g, out=dz_bound[2]["dsb"] if dz_bound is not None else None)
+                if ctx.has_slice_bias and ctx.needs_input_grad[7]:
+                    d_slice_bias = ops.channel_sums(g)
         else:
             dx = ops.cm_to_rows(g)
 

@@ -241,6 +241,18 @@ def recycle_rows(t):
     release_zero_rows(t)
 
 
+def fork_side(device):
+    """Raw handle of the side stream, forked from the current stream here (everything enqueued so far is ordered before
+    what the caller launches on it); join_side must follow before the results are used."""
+    cur, key = _cur_stream_obj(device)
+    side = _side_streams.get(key)
+    if side is None:
+        side = _side_streams[key] = torch.cuda.Stream(device)
+    side.wait_stream(cur)
+    _side_dirty[key] = side
+    return side.cuda_stream
+
+
 def join_side(device):
     """Order the side stream's fills before whatever follows on the current stream."""
     if _side_dirty:
@@ -533,12 +545,13 @@ def rows_to_cm(rows, channels):
     return cm
 
 
-def channel_sums(x, out=None):
-    """Row sums of x (C, N); out: a zeroed (C,) tensor to accumulate into."""
+def channel_sums(x, out=None, side=False):
+    """Row sums of x (C, N); out: a zeroed (C,) tensor to accumulate into.  side: launch on the forked side stream
+    (ops.fork_side; the caller joins with ops.join_side before the result is used)."""
     _f32(x, "x")
     c, n = x.shape
     s = out if out is not None else small_zeros(c, torch.float32, x.device)
-    _lib.call("hpl_channel_sums", x.data_ptr(), c, n, s.data_ptr(), _stream())
+    _lib.call("hpl_channel_sums", x.data_ptr(), c, n, s.data_ptr(), fork_side(x.device) if side else _stream())
     return s
 
 

@@ -230,7 +230,12 @@ def _cur_stream_obj(device):
 def recycle_rows(t):
     """Give back an accumulator whose consumer has been enqueued on the current stream: zeroed here on the side stream
     (large buffers, see above) or already zeroed by the consumer (dispose_mode(t) == 2)."""
+    pool_key = (t.device.index, _stream_of(t.device), t.size(0), t.size(1))
+    if len(_zero_pool.get(pool_key, ())) >= 4:
+        return                       # the pool is full: the buffer is simply dropped (and must not be touched on another stream)
     if t.numel() * 4 >= SIDE_ZERO_MIN_BYTES:
+        # (the buffer stays referenced by the pool, so the allocator cannot reuse its memory while the side-stream fill is
+        # pending; join_side orders the fill before the next use)
         cur, key = _cur_stream_obj(t.device)
         side = _side_streams.get(key)
         if side is None:

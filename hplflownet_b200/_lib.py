@@ -59,6 +59,7 @@ SIGNATURES = {
     "hpl_h16b_bytes": [i64, i64],
     "hpl_h16b_split": [vp, i64, i64, i64, vp, vp, vp, vp],
     "hpl_h16b_split_ex": [vp, i64, i64, i64, vp, vp, vp, vp, i64, cint, vp, vp, vp, vp, cint, vp, vp],
+    "hpl_h16b_splat_csr": [vp, i64, vp, i64, vp, vp, i64, i64, cint, vp, vp, vp, i64, cint, vp, vp, vp, vp, vp, vp],
     "hpl_conv5_workspace": [i64],
     "hpl_conv5_supported": [i64, i64, i64],
     "hpl_conv5": [vp, vp, i64, i64, i64, i64, vp, i64, i64, i64, vp, vp, cint, vp, i64, vp, cint, vp, vp, vp],
@@ -83,7 +84,7 @@ LAUNCHES = {
     "hpl_corr_gather": 1, "hpl_corr_scatter": 1, "hpl_column_sums": 1,
     "hpl_lattice_init_range": 1, "hpl_lattice_points": 1, "hpl_lattice_insert": 6,
     "hpl_lattice_neighbors": 1, "hpl_lattice_corr_table": 1, "hpl_lattice_next_points": 1,
-    "hpl_plan_build": 2, "hpl_h16b_split": 1, "hpl_h16b_split_ex": 1, "hpl_conv5": 3, "hpl_wgrad5": 1,
+    "hpl_plan_build": 2, "hpl_h16b_split": 1, "hpl_h16b_split_ex": 1, "hpl_h16b_splat_csr": 1, "hpl_conv5": 3, "hpl_wgrad5": 1,
 }
 launch_count = 0
 

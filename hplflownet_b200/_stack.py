@@ -76,10 +76,14 @@ def _backward_single_layer5(dx, xs, chans, layer, first_nbr_t, need_input_grad, 
     if need_param_grad and b is not None:
         db = arena["db"] if arena is not None else ops.small_zeros(chans[1], dx.dtype, dx.device)
     dz_amax = arena["dz_amax"] if arena is not None else ops.amax_slots(dx.device, 1)
-    dz16 = ops.h16b_split_ex(dx, chans[1], dz_bound[0], y=xs[1] if act != ops.ACT_NONE else None, act=act,
-                             amax_b=dz_bound[1], amax_out=dz_amax, colsum=db, dispose=1 if keep_fp32 else ops.dispose_mode(dx))
-    if not keep_fp32:
-        ops.recycle_rows(dx)        # (a large accumulator is zeroed on the side stream, under the two gradient kernels)
+    if arena is not None and "_dz16" in arena:                   # (slice backward as a CSR gather: dx was never materialised)
+        assert not keep_fp32
+        dz16 = arena.pop("_dz16")(xs[1] if act != ops.ACT_NONE else None, act, db, dz_amax)
+    else:
+        dz16 = ops.h16b_split_ex(dx, chans[1], dz_bound[0], y=xs[1] if act != ops.ACT_NONE else None, act=act,
+                                 amax_b=dz_bound[1], amax_out=dz_amax, colsum=db, dispose=1 if keep_fp32 else ops.dispose_mode(dx))
+        if not keep_fp32:
+            ops.recycle_rows(dx)    # (a large accumulator is zeroed on the side stream, under the two gradient kernels)
     if arena is not None and "_after_split" in arena:
         arena.pop("_after_split")()                               # (side-stream work the caller deferred to this point)
     grads = [None]

@@ -111,14 +111,27 @@ class _BCLFunction(torch.autograd.Function):
                 # max wsum and zeroes the accumulator again (it returns to the zero pool: no memset per call).
                 if h * c_in * 4 >= ops.SIDE_ZERO_MIN_BYTES:
                     ops.conv5_prepare(layers[0][0])              # weight image on a side stream, under the splat
-                raw = ops.zero_rows(h, c_in, feat.device)
-                z = ops.zero_arena(feat.device, [("wsum", h, torch.float32), ("x_amax", 1, torch.int32), ("w_amax", 1, torch.int32)])
-                lat_amax, wsum_amax = z["x_amax"], z["w_amax"]
-                raw, wsum = ops.scatter_rows(feat, bary_i, off_i, h, True, in_amax=lat_amax, rows=raw, wsum=z["wsum"])
-                inv = torch.empty_like(wsum)
-                x16 = ops.h16b_split_ex(raw, c_in, lat_amax, norm=wsum, inv_out=inv, norm_amax_out=wsum_amax,
-                                        dispose=ops.dispose_mode(raw))
-                ops.recycle_rows(raw)
+                from . import plans
+                splan = plans.splat_plan_for(off_i, h)
+                if splan is not None:
+                    # the splat as a deterministic gather (plans.py: splat plan) fused with the split: the features are
+                    # transposed to point-major rows once (recording max|feat|), then every lattice row is summed from its
+                    # contributions in a fixed order and written straight into the image -- no atomics, no accumulator
+                    z = ops.zero_arena(feat.device, [("x_amax", 1, torch.int32), ("w_amax", 1, torch.int32)])
+                    lat_amax, wsum_amax = z["x_amax"], z["w_amax"]
+                    feat_rows = ops.cm_to_rows(feat, amax=lat_amax)
+                    inv = torch.empty(h, dtype=torch.float32, device=feat.device)
+                    x16 = ops.h16b_splat_csr(feat_rows, c_in, bary_i, splan, lat_amax, normalize=True, inv_out=inv,
+                                             norm_amax_out=wsum_amax)
+                else:
+                    raw = ops.zero_rows(h, c_in, feat.device)
+                    z = ops.zero_arena(feat.device, [("wsum", h, torch.float32), ("x_amax", 1, torch.int32), ("w_amax", 1, torch.int32)])
+                    lat_amax, wsum_amax = z["x_amax"], z["w_amax"]
+                    raw, wsum = ops.scatter_rows(feat, bary_i, off_i, h, True, in_amax=lat_amax, rows=raw, wsum=z["wsum"])
+                    inv = torch.empty_like(wsum)
+                    x16 = ops.h16b_split_ex(raw, c_in, lat_amax, norm=wsum, inv_out=inv, norm_amax_out=wsum_amax,
+                                            dispose=ops.dispose_mode(raw))
+                    ops.recycle_rows(raw)
                 first5 = _stack.First5(x16, lat_amax, plan)
             else:
                 lat, wsum = ops.scatter_rows(feat, bary_i, off_i, h, use_norm)
@@ -177,8 +190,19 @@ class _BCLFunction(torch.autograd.Function):
                 arena = ops.zero_arena(g.device, [("g_amax", 1, torch.int32), ("dz_amax", 1, torch.int32),
                                                   ("dw", w0.numel(), torch.float32), ("db", chans[-1], torch.float32),
                                                   ("dsb", chans[-1], torch.float32)])
-                dx = ops.zero_rows(h, chans[-1], g.device)
-                dx, _ = ops.scatter_rows(g, bary_o, off_o, h, False, in_amax=arena["g_amax"], rows=dx)
+                from . import plans
+                dgrad5_ok = (not ctx.needs_input_grad[1]) or (ctx.first5.plan.symmetric and ops.conv5_supported(w0.size(0), chans[1], chans[0]))
+                splan = plans.splat_plan_for(off_o, h) if dgrad5_ok else None
+                if splan is not None:
+                    # slice backward as a gather over the out tables' splat plan, fused with act', the bias gradient and the
+                    # operand split (see _stack._backward_single_layer5): dz never exists in fp32
+                    g_rows = ops.cm_to_rows(g, amax=arena["g_amax"])
+                    dx = None
+                    arena["_dz16"] = lambda y, act, db, dz_amax: ops.h16b_splat_csr(
+                        g_rows, chans[-1], bary_o, splan, arena["g_amax"], y=y, act=act, amax_b=ctx.wsum_amax, amax_out=dz_amax, colsum=db)
+                else:
+                    dx = ops.zero_rows(h, chans[-1], g.device)
+                    dx, _ = ops.scatter_rows(g, bary_o, off_o, h, False, in_amax=arena["g_amax"], rows=dx)
                 dz_bound = (arena["g_amax"], ctx.wsum_amax, arena)
                 if ctx.has_slice_bias and ctx.needs_input_grad[7]:
                     d_slice_bias = arena["dsb"]

@@ -228,12 +228,28 @@ __device__ __forceinline__ uint32_t bound_bits(const uint32_t* a, const uint32_t
     return (uint32_t)(e + 127) << 23;
 }
 
+// CSR = true: the rows are not read from x but GATHERED -- v = sum over the vertex's splat contributions
+// w(e) * src[point(e), :], csr_ptr / csr_ent = the contributions sorted by vertex (plans.py: splat plan; entry = point |
+// remainder << 30, weight = bary[remainder, point]).  This is the splat (bilateralNN.py:150-182) as a deterministic gather:
+// no atomics, no accumulator, every lattice row written once, straight into the operand image.  norm_self: normalise by the
+// row's own weight sum (computed in the same loop).
+struct CsrArgs {
+    const float* src;            // (n_points, ld_src) point-major source rows
+    long long ld_src;
+    const float* bary;           // (4, n_points)
+    long long n_points;
+    const int* ptr;              // (n_rows + 1)
+    const int* ent;
+    int norm_self;
+};
+
+template <bool CSR>
 __global__ void __launch_bounds__(256)
 h16b_split_fused_kernel(float* __restrict__ x, long long ld, long long n_rows, int channels, int cb_count,
                         const float* __restrict__ norm, float* __restrict__ inv_out, uint32_t* __restrict__ norm_amax_out,
                         const float* __restrict__ y, long long ld_y, float slope, const uint32_t* __restrict__ amax_a,
                         const uint32_t* __restrict__ amax_b, uint32_t* __restrict__ amax_out, float* __restrict__ colsum,
-                        int dispose, uint4* __restrict__ out) {
+                        int dispose, uint4* __restrict__ out, const CsrArgs csr) {
     __shared__ float part[256][9];
     const int cpr = cb_count * 4;                                         // 8-channel groups per row
     const int rows_per_iter = 256 / cpr;
@@ -252,9 +268,30 @@ h16b_split_fused_kernel(float* __restrict__ x, long long ld, long long n_rows, i
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = 0.f;
-        float* p = x + row * ld + c0;
+        float* p = CSR ? nullptr : x + row * ld + c0;
         const bool full8 = c0 + 8 <= channels;
-        if (full8) {
+        float w_self = 0.f;
+        if (CSR) {
+            // the 8 threads of a row read one contiguous source row per contribution (8 x 32 B); contributions in the plan's
+            // fixed order -> the sum is reproducible
+            const int e1 = __ldg(csr.ptr + row + 1);
+            for (int e = __ldg(csr.ptr + row); e < e1; ++e) {
+                const int ent = __ldg(csr.ent + e);
+                const long long pt = ent & 0x3fffffff;
+                const float w = __ldg(csr.bary + (long long)((unsigned)ent >> 30) * csr.n_points + pt);
+                const float* q = csr.src + pt * csr.ld_src + c0;
+                if (full8) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(q)), b = __ldg(reinterpret_cast<const float4*>(q + 4));
+                    v[0] = fmaf(w, a.x, v[0]); v[1] = fmaf(w, a.y, v[1]); v[2] = fmaf(w, a.z, v[2]); v[3] = fmaf(w, a.w, v[3]);
+                    v[4] = fmaf(w, b.x, v[4]); v[5] = fmaf(w, b.y, v[5]); v[6] = fmaf(w, b.z, v[6]); v[7] = fmaf(w, b.w, v[7]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (c0 + i < channels) v[i] = fmaf(w, __ldg(q + i), v[i]);
+                }
+                w_self += w;
+            }
+        } else if (full8) {
             const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
             v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
         } else {
@@ -262,8 +299,8 @@ h16b_split_fused_kernel(float* __restrict__ x, long long ld, long long n_rows, i
             for (int i = 0; i < 8; ++i)
                 if (c0 + i < channels) v[i] = p[i];
         }
-        if (norm != nullptr) {
-            const float w = __ldg(norm + row);
+        if (norm != nullptr || (CSR && csr.norm_self)) {
+            const float w = (CSR && csr.norm_self) ? w_self : __ldg(norm + row);
             const float r = 1.0f / (w + 1e-5f);
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] *= r;                         // same rounding as normalize_rows_kernel
@@ -280,7 +317,7 @@ h16b_split_fused_kernel(float* __restrict__ x, long long ld, long long n_rows, i
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] += v[i];
-        if (dispose != 0) {
+        if (!CSR && dispose != 0) {
             const float z = dispose == 2 ? 0.f : 1.f;
             if (full8) {
                 *reinterpret_cast<float4*>(p) = make_float4(v[0] * z, v[1] * z, v[2] * z, v[3] * z);
@@ -1173,9 +1210,37 @@ int hpl_h16b_split_ex(float* x, int64_t ld, int64_t n_rows, int64_t channels, co
     const long long cap = 8LL * num_sms();                                // grid-stride: few atomics per column sum
     if (blocks > cap) blocks = cap;
     const float slope = act == HPL_ACT_LEAKY ? HPL_LEAKY_RATE : 0.f;
-    h16b_split_fused_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+    h16b_split_fused_kernel<false><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
         x, ld, n_rows, (int)channels, cb, norm, inv_out, norm_amax_out, act == HPL_ACT_NONE ? nullptr : y, ld_y, slope, amax_a, amax_b,
-        amax_out, colsum, dispose, reinterpret_cast<uint4*>(x16));
+        amax_out, colsum, dispose, reinterpret_cast<uint4*>(x16), CsrArgs{});
+    HPL_RETURN_LAST();
+}
+
+/* The splat (bilateralNN.py:150-182) and the slice backward (:226-232 autograd) as a deterministic GATHER fused with the operand split:
+ *   row v of the image <- split( post( sum_{e in [csr_ptr[v], csr_ptr[v+1])} bary[r(e), pt(e)] * src[pt(e), :] ) )
+ * csr_ent[e] = pt | r << 30 (contributions sorted by vertex: the splat plan), src (n_points, ld_src) point-major.
+ * post: normalize != 0 -> divide by (the row's weight sum + 1e-5), inv_out[v] <- that reciprocal, norm_amax_out <- max weight sum;
+ *       y / act -> multiply by act'(y[v, :]); colsum += column sums; scale from *amax_a (x *amax_b), amax_out as hpl_h16b_split_ex. */
+int hpl_h16b_splat_csr(const float* src, int64_t ld_src, const float* bary, int64_t n_points, const int32_t* csr_ptr,
+                       const int32_t* csr_ent, int64_t n_rows, int64_t channels, int normalize, float* inv_out,
+                       uint32_t* norm_amax_out, const float* y, int64_t ld_y, int act, const uint32_t* amax_a, const uint32_t* amax_b,
+                       uint32_t* amax_out, float* colsum, void* x16, void* stream) {
+    HPL_CHECK_ARG((src && bary && csr_ptr && csr_ent) || n_rows == 0);
+    HPL_CHECK_ARG(amax_a && x16 && channels > 0 && ld_src >= channels && ld_src % 4 == 0 && n_points < (1LL << 30));
+    HPL_CHECK_ARG(((uintptr_t)src & 15) == 0 && ((uintptr_t)x16 & 15) == 0);
+    HPL_CHECK_ARG(act == HPL_ACT_NONE || (y != nullptr && ld_y >= channels));
+    HPL_CHECK_ARG(cb_of(channels) * 4 <= 256);
+    if (n_rows == 0) return 0;
+    const int cb = cb_of(channels);
+    const int rows_per_iter = 256 / (cb * 4);
+    long long blocks = (n_rows + rows_per_iter - 1) / rows_per_iter;
+    const long long cap = 16LL * num_sms();                               // grid-stride: few atomics per column sum
+    if (blocks > cap) blocks = cap;
+    const float slope = act == HPL_ACT_LEAKY ? HPL_LEAKY_RATE : 0.f;
+    CsrArgs c{src, ld_src, bary, n_points, csr_ptr, csr_ent, normalize};
+    h16b_split_fused_kernel<true><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+        nullptr, 0, n_rows, (int)channels, cb, nullptr, inv_out, norm_amax_out, act == HPL_ACT_NONE ? nullptr : y, ld_y, slope, amax_a,
+        amax_b, amax_out, colsum, 0, reinterpret_cast<uint4*>(x16), c);
     HPL_RETURN_LAST();
 }
 

@@ -663,6 +663,22 @@ def wgrad5(x16, dz16, plan, c_in, c_out, x_amax, dz_amax, out=None):
     return dw
 
 
+def h16b_splat_csr(src, channels, bary, splan, amax_a, normalize=False, inv_out=None, norm_amax_out=None, y=None, act=ACT_NONE,
+                   amax_b=None, amax_out=None, colsum=None):
+    """Splat as a deterministic gather fused with the operand split (include/hplflownet_b200.h: hpl_h16b_splat_csr).
+    src (N, ld) point-major rows (ops.cm_to_rows), bary (4, N), splan: plans.SplatPlan.  Returns the h16b image."""
+    _f32(src, "src"); _f32(bary, "bary")
+    h = splan.n_rows
+    buf = torch.empty(max(_lib.load().hpl_h16b_bytes(h, channels), 16), dtype=torch.uint8, device=src.device)
+    ptr = lambda t: t.data_ptr() if t is not None else None      # noqa: E731
+    has_y = y is not None and act != ACT_NONE
+    _lib.call("hpl_h16b_splat_csr", src.data_ptr(), src.stride(0), bary.data_ptr(), splan.n_points, splan.ptr.data_ptr(),
+              splan.ent.data_ptr(), h, channels, int(bool(normalize)), ptr(inv_out), ptr(norm_amax_out),
+              y.data_ptr() if has_y else None, y.stride(0) if has_y else 0, act if has_y else ACT_NONE,
+              amax_a.data_ptr(), ptr(amax_b), ptr(amax_out), ptr(colsum), buf.data_ptr(), _stream())
+    return buf
+
+
 def h16b_split_ex(x, channels, amax_a, norm=None, inv_out=None, norm_amax_out=None, y=None, act=ACT_NONE, amax_b=None,
                   amax_out=None, colsum=None, dispose=0):
     """h16b image of x with the surrounding passes folded in (include/hplflownet_b200.h: hpl_h16b_split_ex)."""

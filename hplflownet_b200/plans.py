@@ -188,3 +188,83 @@ def prepare(blur_neighbors):
 
 def clear():
     _cache.clear()
+    _splat_cache.clear()
+
+
+# ------------------------------------------------------------------------------------------ splat plans
+# The splat's scatter pattern -- lattice_offset (d+1, N): point -> its d+1 lattice rows -- is a per-lattice constant like the
+# neighbour table.  Sorted by row it turns the splat (and the backward of the slice over the same tables) into a gather:
+# csr_ptr[v] .. csr_ptr[v+1] index the contributions (point, remainder) of lattice row v, in a fixed order (ascending
+# remainder, then point), so the fp32 sums are reproducible and no atomics or accumulators are needed
+# (hpl_h16b_splat_csr).  Built with a stable device sort on the tensor's SECOND use (or plans.prepare_splat), cached like the
+# tile plans.
+# Off by default: measured on cfg2 x 32 the gather (166 us: latency-bound loops over 4.3 contributions per row on average but
+# up to 220 on dense rows) plus the transposition of the features (50 us) is twice the cost of the RED splat + split (74 +
+# 29 us).  Worth it where bitwise reproducible splats matter: plans.SPLAT_PLANS = True.
+SPLAT_PLANS = False
+
+
+class SplatPlan:
+    def __init__(self, ptr, ent, n_rows, n_points):
+        self.ptr, self.ent, self.n_rows, self.n_points = ptr, ent, n_rows, n_points
+
+
+_splat_cache = {}
+
+
+def build_splat(off2, n_rows):
+    """off2: (d+1, N) int32 / int64 CUDA tensor of lattice rows (entries outside [0, n_rows) are dropped, as in the kernels)."""
+    d1, n = off2.shape
+    if n >= (1 << 30):
+        return None
+    keys = off2.reshape(-1).to(torch.int64)
+    keys = torch.where((keys >= 0) & (keys < n_rows), keys, torch.full_like(keys, n_rows))
+    order = torch.argsort(keys, stable=True)                              # position r * N + point, grouped by row
+    counts = torch.bincount(keys, minlength=n_rows + 1)[:n_rows]
+    ptr = torch.zeros(n_rows + 1, dtype=torch.int32, device=off2.device)
+    ptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+    ent = ((order % n) | ((order // n) << 30)).to(torch.int32)            # point | remainder << 30 (dropped entries trail, unused)
+    return SplatPlan(ptr.contiguous(), ent.contiguous(), n_rows, n)
+
+
+def _splat_key(off2, n_rows):
+    return (off2.data_ptr(), tuple(off2.shape), off2.dtype, off2.device, int(n_rows))
+
+
+def splat_plan_for(off2, n_rows):
+    """Cached splat plan of an offset tensor, or None while it has been seen only once (see PLAN_ON_FIRST_USE)."""
+    if not SPLAT_PLANS:
+        return None
+    key = _splat_key(off2, n_rows)
+    ent = _splat_cache.get(key)
+    fresh = ent is None or ent[0]() is None or ent[1] != off2._version
+    if not fresh and ent[2] is not None:
+        return ent[2]
+    plan = None
+    if not fresh or PLAN_ON_FIRST_USE:
+        plan = build_splat(off2, n_rows)
+    base = off2._base if off2._base is not None else off2
+    try:
+        ref = weakref.ref(base, lambda _r, k=key: _splat_cache.pop(k, None))
+    except TypeError:
+        return plan
+    _splat_cache[key] = (ref, off2._version, plan)
+    return plan
+
+
+def prepare_splat(lattice_offset, n_rows):
+    """Plan a lattice_offset tensor now (accepts the module-level (1, d+1, N) tensor or its (d+1, N) view)."""
+    off2 = lattice_offset[0] if lattice_offset.dim() == 3 else lattice_offset
+    off2 = off2.contiguous()
+    key = _splat_key(off2, n_rows)
+    ent = _splat_cache.get(key)
+    if ent is not None and ent[0]() is not None and ent[1] == off2._version and ent[2] is not None:
+        return ent[2]
+    plan = build_splat(off2, n_rows)
+    base = off2._base if off2._base is not None else off2
+    try:
+        ref = weakref.ref(base, lambda _r, k=key: _splat_cache.pop(k, None))
+        _splat_cache[key] = (ref, off2._version, plan)
+    except TypeError:
+        pass
+    return plan

@@ -203,6 +203,18 @@ int hpl_h16b_split_ex(float* x, int64_t ld, int64_t n_rows, int64_t channels, co
                       const uint32_t* amax_b, uint32_t* amax_out, float* colsum, int dispose, void* x16,
                       void* stream);
 
+/* The splat (bilateralNN.py:150-182) -- and the backward of the slice (:226-232) -- as a deterministic GATHER fused with the
+ * operand split: no atomics, no fp32 accumulator, every lattice row is written once, straight into the h16b image.
+ *   row v <- split( post( sum_{e in [csr_ptr[v], csr_ptr[v+1])} bary[r(e), pt(e)] * src[pt(e), :] ) )
+ * csr_ptr (n_rows + 1), csr_ent[e] = pt | r << 30: the splat contributions sorted by vertex (fixed order -> reproducible
+ * sums); src (n_points, ld_src): the point features / upstream gradient, point-major (hpl_cm_to_rows).
+ * post: normalize != 0 -> divide by (the row's weight sum + 1e-5), inv_out[v] <- that reciprocal, norm_amax_out <- max weight
+ * sum; y / act -> activation backward; colsum, amax_a / amax_b / amax_out as in hpl_h16b_split_ex. */
+int hpl_h16b_splat_csr(const float* src, int64_t ld_src, const float* bary, int64_t n_points, const int32_t* csr_ptr,
+                       const int32_t* csr_ent, int64_t n_rows, int64_t channels, int normalize, float* inv_out,
+                       uint32_t* norm_amax_out, const float* y, int64_t ld_y, int act, const uint32_t* amax_a,
+                       const uint32_t* amax_b, uint32_t* amax_out, float* colsum, void* x16, void* stream);
+
 /* The weight part of hpl_conv5 alone: max|w| and the tile image of w into `workspace` (hpl_conv5_workspace bytes).  Lets a
  * caller build it ahead of time -- on another stream, while the splat runs -- and call hpl_conv5 with workspace_valid = 1. */
 int hpl_conv5_weights(const float* w, int64_t w_sf, int64_t w_sc, int64_t w_so, int64_t filter_size, int64_t c_in,

@@ -317,3 +317,32 @@ def test_graph_replay_of_the_step_matches_eager_launches():
             scale = b.abs().max().item()
             # (fp32 RED accumulation order differs from run to run: not bitwise)
             assert (a - b).abs().max().item() <= 2e-5 * scale + 1e-12, "tensor %d of trial %d: %g vs scale %g" % (i, trial, (a - b).abs().max().item(), scale)
+
+
+def test_deterministic_splat_plans(monkeypatch):
+    """plans.SPLAT_PLANS: the splat and the slice backward as CSR gathers fused with the operand split
+    (hpl_h16b_splat_csr) -- same results as the RED splat within the fp32 budget, and bitwise identical from run to run."""
+    from hplflownet_b200 import plans
+    import bench
+    mod = bench.make_state().to(DEV)
+    _, res, gy, n_tot, h_tot = bench.make_batch(torch.device(DEV), [40, 41, 42])
+    plans.prepare(res["blur_neighbors"])
+    params = list(mod.parameters())
+
+    def step():
+        for p in params:
+            p.grad = None
+        res["features"].grad = None
+        y = mod(res["features"], res["barycentric"], res["lattice_offset"], res["blur_neighbors"], res["barycentric"], res["lattice_offset"])
+        y.backward(gy)
+        return [y.detach().clone(), res["features"].grad.clone()] + [p.grad.clone() for p in params]
+
+    want = step()
+    monkeypatch.setattr(plans, "SPLAT_PLANS", True)
+    assert plans.prepare_splat(res["lattice_offset"], h_tot) is not None
+    got1, got2 = step(), step()
+    for i, (a, b, c) in enumerate(zip(got1, want, got2)):
+        scale = b.abs().max().item()
+        assert (a - b).abs().max().item() <= 2e-5 * scale, "tensor %d: %g vs scale %g" % (i, (a - b).abs().max().item(), scale)
+    # the forward (splat -> conv -> slice) has no atomics left: bitwise reproducible
+    assert torch.equal(got1[0], got2[0])
